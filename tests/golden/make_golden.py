@@ -1,0 +1,206 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ from the UNMODIFIED reference.
+
+Runs only in the build container, where the reference is mounted read-only at
+/root/reference (it does not exist on the GPU box -- tests read the committed .npz files).
+
+    PYTHONDONTWRITEBYTECODE=1 OPENBLAS_NUM_THREADS=1 OMP_NUM_THREADS=1 \
+        python tests/golden/make_golden.py instances small l512 l2048 l1152
+
+Fixtures
+  instances.npz       coupling lists of droplet instances 001-003 (L=128), 001 (L=512, 1152, 2048), J124 C8 #1,
+                      with the matching lines of groundstates_otn2d.txt / results_*.txt
+  ref_small.npz       L=128 #1: search_ground_state / spectrum / Gibbs outputs for several (rot, precondition, D)
+                      plus per-site traces (marginals of every branch, branch records after merge + top-M)
+  ref_l512.npz        config 2: L=512 #1, M=2^10, Dmax=16
+  ref_l2048.npz       config 4 (M=2^10 variant): L=2048 #1, Dmax=32
+  ref_l1152.npz       config 3: L=1152 #1 spectrum (ee=1, dE=1) -> number of decoded states, energies
+"""
+import os
+import sys
+import time
+import logging
+import warnings
+
+import numpy as np
+
+if not hasattr(np, 'int'):       # the reference still uses np.int on the ee=3 path (tnac4o.py:2213)
+    np.int = int
+sys.path.insert(0, '/root/reference')
+sys.dont_write_bytecode = True
+warnings.filterwarnings('ignore')
+logging.disable(logging.CRITICAL)
+import tnac4o as ref   # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+INST = '/root/reference/instances'
+SHAPES = {128: (4, 4), 512: (8, 8), 1152: (12, 12), 2048: (16, 16)}
+
+
+def raw_couplings(L, k):
+    return np.loadtxt('%s/Chimera_droplet_instances/chimera%d_spinglass_power/%03d.txt' % (INST, L, k))
+
+
+def droplet_J(L, k):
+    fn = '%s/Chimera_droplet_instances/chimera%d_spinglass_power/%03d.txt' % (INST, L, k)
+    return ref.round_Jij(ref.Jij_f2p(ref.load_Jij(fn)), 1 / 75)
+
+
+def golden_line(L, k):
+    fn = '%s/Chimera_droplet_instances/chimera%d_spinglass_power/groundstates_otn2d.txt' % (INST, L)
+    with open(fn) as f:
+        for line in f:
+            name, rest = line.split(':')
+            if name.strip() == '%03d.txt' % k:
+                vals = rest.split()
+                return float(vals[0]), np.array(vals[1:], dtype=np.int8)
+    raise KeyError(k)
+
+
+def make_instances():
+    out = {}
+    for L, ks in ((128, (1, 2, 3)), (512, (1,)), (1152, (1,)), (2048, (1,))):
+        for k in ks:
+            raw = raw_couplings(L, k)
+            out['J_%d_%03d_i' % (L, k)] = raw[:, 0].astype(np.int32)
+            out['J_%d_%03d_j' % (L, k)] = raw[:, 1].astype(np.int32)
+            out['J_%d_%03d_v' % (L, k)] = raw[:, 2].astype(np.float64)
+            e, bits = golden_line(L, k)
+            out['gs_%d_%03d_energy' % (L, k)] = np.float64(e)
+            out['gs_%d_%03d_bits' % (L, k)] = bits
+    raw = np.loadtxt('%s/Chimera_J124/C=8_J124/001.txt' % INST)
+    out['J124_C8_001_i'] = raw[:, 0].astype(np.int32)
+    out['J124_C8_001_j'] = raw[:, 1].astype(np.int32)
+    out['J124_C8_001_v'] = raw[:, 2].astype(np.float64)
+    out['J124_C8_001_energy_deg'] = np.array([-2309, 1152], dtype=np.int64)    # results file / test_examples.py:142
+    np.savez_compressed(os.path.join(HERE, 'instances.npz'), **out)
+
+
+def result_fields(ins, tag, out):
+    out[tag + '_energy'] = np.asarray(ins.energy)
+    out[tag + '_states'] = np.asarray(ins.states)
+    out[tag + '_probability'] = np.asarray(ins.probability)
+    out[tag + '_degeneracy'] = np.int64(ins.degeneracy)
+    out[tag + '_discarded'] = np.float64(ins.discarded_probability)
+    out[tag + '_negative'] = np.float64(ins.negative_probability)
+    out[tag + '_bits'] = ins.binary_states()
+
+
+def make_small():
+    out = {}
+    J = droplet_J(128, 1)
+    for rot, pre, D, M in ((0, False, 8, 256), (3, False, 8, 256), (0, True, 8, 256), (1, True, 16, 1024), (0, False, 48, 1024)):
+        ins = ref.tnac4o(mode='Ising', Nx=4, Ny=4, Nc=8, J=J, beta=3)
+        if rot:
+            ins.rotate_graph(rot)
+        if pre:
+            ins.precondition(mode='balancing')
+        tag = 'gs_r%d_p%d_D%d_M%d' % (rot, pre, D, M)
+        trace = []
+        if (rot, pre, D) == (0, False, 8):
+            orig = ins._calculate_Pn
+
+            def spy(A, RL, AT, RR, _o=orig):
+                P, flag = _o(A, RL, AT, RR)
+                trace.append((P.copy(), flag))
+                return P, flag
+            ins._calculate_Pn = spy
+        ins.search_ground_state(M=M, relative_P_cutoff=1e-8, Dmax=D)
+        result_fields(ins, tag, out)
+        if trace:
+            # every 11th marginal (call order = site-major, branch-minor) keeps the fixture small
+            out[tag + '_trace_stride'] = np.int64(11)
+            out[tag + '_trace_calls'] = np.int64(len(trace))
+            out[tag + '_trace_P'] = np.array([t[0] for t in trace[::11]])
+            out[tag + '_trace_flag'] = np.array([t[1] for t in trace], dtype=np.float64)
+            out[tag + '_rhoT_overlap'] = np.array(ins.rhoT_overlap, dtype=np.float64)
+            out[tag + '_rhoT_discarded'] = np.array(ins.rhoT_discarded, dtype=np.float64)
+    # spectrum + decode (test_examples.py:59-104 expects 31 states below dE = 1)
+    for rot in (0, 1):
+        ins = ref.tnac4o(mode='Ising', Nx=4, Ny=4, Nc=8, J=J, beta=3)
+        if rot:
+            ins.rotate_graph(rot)
+        ins.search_low_energy_spectrum(excitations_encoding=1, M=1024, relative_P_cutoff=1e-8, Dmax=16, max_dEng=1.0)
+        ins.decode_low_energy_states(max_dEng=1.0, max_states=2 ** 20)
+        tag = 'sp_r%d' % rot
+        order = np.lexsort(ins.states.T[::-1])
+        out[tag + '_energy'] = ins.energy[order]
+        out[tag + '_states'] = ins.states[order]
+        out[tag + '_energy_Jij'] = ref.energy_Jij(J, ins.binary_states())[order]
+    # Gibbs sampling with the global numpy stream (test_examples.py:36-56)
+    ins = ref.tnac4o(mode='Ising', Nx=4, Ny=4, Nc=8, J=J, beta=1)
+    np.random.seed(1)
+    ins.gibbs_sampling(M=128, Dmax=16)
+    out['gibbs_energy'] = ins.energy
+    out['gibbs_states'] = ins.states.astype(np.int16)
+    out['gibbs_negative'] = np.float64(ins.negative_probability)
+    # J124 C8 #1 is the strongest exact known answer (degeneracy counting), but takes minutes: see `j124`
+    np.savez_compressed(os.path.join(HERE, 'ref_small.npz'), **out)
+
+
+def make_big(L, D, M, name):
+    Nx, Ny = SHAPES[L]
+    ins = ref.tnac4o(mode='Ising', Nx=Nx, Ny=Ny, Nc=8, J=droplet_J(L, 1), beta=3)
+    calls = [0]
+    orig = ins._calculate_Pn
+
+    def spy(A, RL, AT, RR):
+        calls[0] += 1
+        return orig(A, RL, AT, RR)
+    ins._calculate_Pn = spy
+    t0 = time.time()
+    ins._setup_rhoT(Dmax=D)
+    t_rho = time.time() - t0
+    setup = ins._setup_rhoT
+    ins._setup_rhoT = lambda **kw: None          # already built; time the search phase separately
+    t0 = time.time()
+    ins.search_ground_state(M=M, relative_P_cutoff=1e-8, Dmax=D)
+    t_search = time.time() - t0
+    ins._setup_rhoT = setup
+    out = {}
+    result_fields(ins, 'gs', out)
+    out['seconds_rhoT'], out['seconds_search'] = np.float64(t_rho), np.float64(t_search)
+    out['marginals'] = np.int64(calls[0])
+    out['rhoT_overlap'] = np.array(ins.rhoT_overlap, dtype=np.float64)
+    out['rhoT_discarded'] = np.array(ins.rhoT_discarded, dtype=np.float64)
+    out['params'] = np.array([L, D, M], dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, name), **out)
+
+
+def make_l1152():
+    ins = ref.tnac4o(mode='Ising', Nx=12, Ny=12, Nc=8, J=droplet_J(1152, 1), beta=3)
+    t0 = time.time()
+    ins.search_low_energy_spectrum(excitations_encoding=1, M=1024, relative_P_cutoff=1e-8, Dmax=32, max_dEng=1.0)
+    t_search = time.time() - t0
+    out = {}
+    result_fields(ins, 'gs', out)
+    out['n_shapes'] = np.int64(len(ins.d))
+    t0 = time.time()
+    ins.decode_low_energy_states(max_dEng=1.0, max_states=2 ** 20)
+    out['seconds_search'], out['seconds_decode'] = np.float64(t_search), np.float64(time.time() - t0)
+    out['n_states'] = np.int64(len(ins.energy))
+    out['energies_sorted_head'] = np.sort(ins.energy)[:4096]
+    vals, counts = np.unique(np.round((ins.energy - ins.energy[0]) * 75).astype(np.int64), return_counts=True)
+    out['level_75dE'], out['level_count'] = vals, counts
+    np.savez_compressed(os.path.join(HERE, 'ref_l1152.npz'), **out)
+
+
+def make_j124():
+    raw = np.loadtxt('%s/Chimera_J124/C=8_J124/001.txt' % INST)
+    J = [[int(r[0]) - 1, int(r[1]) - 1, float(r[2])] for r in raw]
+    out = {}
+    ins = ref.tnac4o(mode='Ising', Nx=8, Ny=8, Nc=8, J=J, beta=0.75)
+    ins.precondition(mode='balancing')
+    ins.search_ground_state(M=2 ** 12, relative_P_cutoff=1e-8, Dmax=8)
+    result_fields(ins, 'gs', out)
+    np.savez_compressed(os.path.join(HERE, 'ref_j124.npz'), **out)
+
+
+if __name__ == '__main__':
+    for what in sys.argv[1:]:
+        t0 = time.time()
+        {'instances': make_instances, 'small': make_small,
+         'l512': lambda: make_big(512, 16, 1024, 'ref_l512.npz'),
+         'l2048': lambda: make_big(2048, 32, 1024, 'ref_l2048.npz'),
+         'l1152': make_l1152, 'j124': make_j124}[what]()
+        print(what, 'done in %.1f s' % (time.time() - t0), flush=True)

@@ -1,0 +1,67 @@
+"""CPU tests of the drop-in boundary: the shared library loads and exports every symbol include/tnac4o_b200.h
+declares, the product fails loudly without a GPU, and the product never imports the oracle."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, 'include', 'tnac4o_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(tn_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import tnac4o_b200._native as nat
+    declared = header_symbols()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(nat.lib, name), name
+    assert sorted(nat.EXPORTED) == declared
+    assert nat.lib.tn_version() >= 100
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    import tnac4o_b200
+    from conftest import droplet_couplings
+    ins = tnac4o_b200.tnac4o(mode='Ising', Nx=4, Ny=4, Nc=8, J=droplet_couplings(128), beta=3)
+    with pytest.raises(RuntimeError):
+        ins.search_ground_state(M=16, Dmax=4)
+    with pytest.raises(RuntimeError):
+        tnac4o_b200.energy_Jij(droplet_couplings(128), [[1] * 128])
+
+
+def test_product_does_not_import_oracle():
+    code = "import sys; import tnac4o_b200; assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)"
+    subprocess.run([sys.executable, '-c', code], check=True, cwd=ROOT)
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'tnac4o_b200')):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh')):
+                assert 'oracle' not in open(os.path.join(dirpath, f)).read().replace('no oracle', ''), f
+
+
+def test_host_model_tables_match_oracle(J128=None):
+    """host-side prep of the product (tnac4o_b200/model.py) against the oracle's restatement, bit for bit"""
+    import numpy as np
+    from conftest import droplet_couplings
+    from oracle import RefSolver
+    from tnac4o_b200.model import IsingLattice, upper_triangular
+    J = droplet_couplings(128)
+    ref = RefSolver(mode='Ising', Nx=4, Ny=4, Nc=8, J=J, beta=3)
+    lat = IsingLattice(upper_triangular(J, 128), 4, 4, 8)
+    for ny in range(4):
+        for nx in range(4):
+            for a, b in zip(lat.energy_tables(ny, nx), ref.energy_tables(ny, nx)):
+                assert np.array_equal(a, b)
+            Wc, dm, rm = lat.boltzmann(ny, nx, 3, ref.Xu[ny][nx], ref.Xl[ny][nx], ref.Xr[ny][nx], ref.Xd[ny][nx])
+            Wr, dr, rr = ref.site_weights(ny, nx)
+            assert np.array_equal(Wc, Wr) and np.array_equal(dm, dr) and np.array_equal(rm, rr)
+            assert np.array_equal(lat.traced(Wc, dm, rm, 2 ** lat.sd[ny][nx], 2 ** lat.sr[ny][nx]), ref.traced_mpo(ny, nx))

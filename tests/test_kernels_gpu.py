@@ -1,0 +1,187 @@
+"""GPU parity tests of the individual sm_100a kernels against numpy / the oracle (called through the C ABI)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device('cuda', 0)
+
+
+def up(a, dtype=None):
+    return torch.from_numpy(np.ascontiguousarray(a if dtype is None else a.astype(dtype))).to(dev())
+
+
+@pytest.mark.parametrize('M,N,K', [(1, 1, 1), (7, 5, 3), (64, 64, 16), (130, 70, 33), (512, 512, 512), (1024, 257, 96),
+                                   (32, 480, 8192), (16, 16, 4096), (2048, 128, 512), (57, 59, 39)])
+@pytest.mark.parametrize('tA,tB', [(False, False), (True, False), (False, True), (True, True)])
+def test_gemm(M, N, K, tA, tB):
+    from tnac4o_b200 import ops
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    A = rng.standard_normal((K, M) if tA else (M, K))
+    B = rng.standard_normal((N, K) if tB else (K, N))
+    C = ops.gemm(up(A), up(B), transA=tA, transB=tB).cpu().numpy()
+    ref = (A.T if tA else A) @ (B.T if tB else B)
+    assert np.max(np.abs(C - ref)) <= 1e-12 * max(1.0, np.max(np.abs(ref))) * np.sqrt(K)
+
+
+def test_gemm_alpha_beta_and_strided_views():
+    from tnac4o_b200 import ops
+    rng = np.random.default_rng(5)
+    A, B, C0 = rng.standard_normal((100, 40)), rng.standard_normal((40, 90)), rng.standard_normal((100, 64))
+    out = up(C0)
+    ops.gemm(up(A), up(B)[:, :64], out=out, alpha=-1.0, beta=1.0)
+    assert np.max(np.abs(out.cpu().numpy() - (C0 - A @ B[:, :64]))) < 1e-12
+
+
+@pytest.mark.parametrize('m,n', [(1, 1), (5, 3), (33, 70), (300, 7)])
+def test_transpose(m, n):
+    from tnac4o_b200 import ops
+    A = np.random.default_rng(0).standard_normal((m, n))
+    assert np.array_equal(ops.transpose(up(A)).cpu().numpy(), A.T)
+
+
+def _check_qr(A, tol=1e-13):
+    from tnac4o_b200 import ops
+    from oracle import ref_qr
+    m, n = A.shape
+    k = min(m, n)
+    Q, R, bits = ops.qr_pos(up(A).clone())
+    Q, R = Q.cpu().numpy(), R.cpu().numpy()
+    scale = max(1.0, np.max(np.abs(A)))
+    assert Q.shape == (m, k) and R.shape == (k, n)
+    assert np.all(np.diag(R) >= 0)
+    assert np.max(np.abs(np.tril(R, -1))) == 0
+    assert np.max(np.abs(Q.T @ Q - np.eye(k))) < tol * 10 * np.sqrt(m)
+    assert np.max(np.abs(Q @ R - A)) < tol * 10 * scale * np.sqrt(m)
+    assert np.float64(np.max(np.abs(R))).view(np.int64) == int(bits.item())
+    return Q, R
+
+
+@pytest.mark.parametrize('m,n', [(1, 1), (2, 1), (16, 16), (16, 512), (256, 512), (40, 12), (512, 32), (1024, 64),
+                                 (2048, 128), (2048, 512), (8192, 512), (100, 57), (17, 5), (129, 130)])
+def test_qr_random(m, n):
+    from oracle import ref_qr
+    A = np.random.default_rng(m + n).standard_normal((m, n))
+    Q, R = _check_qr(A)
+    Qr, Rr = ref_qr(A)
+    assert np.max(np.abs(R - Rr)) < 1e-10 * np.sqrt(m)       # full column rank: QR with diag(R) > 0 is unique
+
+
+def test_qr_graded_and_rank_deficient():
+    rng = np.random.default_rng(3)
+    U, _ = np.linalg.qr(rng.standard_normal((600, 64)))
+    V, _ = np.linalg.qr(rng.standard_normal((64, 64)))
+    A = (U * np.logspace(0, -17, 64)) @ V.T                  # singular values over 17 decades, like the boundary MPS
+    _check_qr(A)
+    B = np.zeros((300, 40))
+    B[:, :10] = rng.standard_normal((300, 10))
+    B[:, 20:30] = B[:, :10] @ rng.standard_normal((10, 10))   # exactly dependent and exactly zero columns
+    _check_qr(B)
+    _check_qr(np.zeros((50, 8)))
+
+
+def _check_svd(C, rel_sv_tol=1e-10):
+    from tnac4o_b200 import ops
+    m, n = C.shape
+    k = min(m, n)
+    U, S, Vt = ops.svd(up(C), want_vectors=True)
+    U, S, Vt = U.cpu().numpy(), S.cpu().numpy(), Vt.cpu().numpy()
+    S_only = ops.svd(up(C), want_vectors=False).cpu().numpy()
+    Sr = np.linalg.svd(C, compute_uv=False)
+    nrm = max(Sr[0], 1e-300)
+    assert np.all(np.diff(S) <= 0)
+    assert np.max(np.abs(S - Sr)) < 1e-13 * nrm * np.sqrt(max(m, n))
+    assert np.max(np.abs(S_only - Sr)) < 1e-13 * nrm * np.sqrt(max(m, n))
+    assert np.max(np.abs((U * S) @ Vt - C)) < 1e-13 * nrm * max(m, n)
+    live = S > 1e-300
+    assert np.max(np.abs((U.T @ U - np.eye(k))[np.ix_(live, live)])) < 1e-12 * np.sqrt(max(m, n))
+    assert np.max(np.abs(Vt @ Vt.T - np.eye(k))) < 1e-12 * np.sqrt(max(m, n))
+    return S
+
+
+@pytest.mark.parametrize('m,n', [(1, 1), (2, 2), (3, 5), (16, 16), (32, 32), (64, 64), (16, 256), (16, 512), (57, 57),
+                                 (128, 128), (256, 256), (512, 512), (39, 64)])
+def test_svd_random(m, n):
+    _check_svd(np.random.default_rng(m * 3 + n).standard_normal((m, n)))
+
+
+@pytest.mark.parametrize('k', [32, 128, 512])
+def test_svd_graded_spectrum_relative_accuracy(k):
+    """singular values spanning 16 decades (what truncateC sees, mps.py:804-806): small ones must stay accurate"""
+    rng = np.random.default_rng(k)
+    U, _ = np.linalg.qr(rng.standard_normal((k, k)))
+    V, _ = np.linalg.qr(rng.standard_normal((k, k)))
+    s = np.logspace(0, -16, k)
+    C = np.triu((U * s) @ V.T @ np.diag(np.logspace(0, -3, k)))      # graded upper-triangular, like an R factor
+    S = _check_svd(C)
+    exact = np.linalg.svd(C.astype(np.longdouble).astype(np.float64), compute_uv=False)
+    big = exact > 1e-9 * exact[0]
+    assert np.max(np.abs(S[big] / exact[big] - 1)) < 1e-6
+
+
+def test_truncation_rank_and_nfactor():
+    from tnac4o_b200 import ops
+    from oracle import ref_nfactor
+    S = np.array([1.0, 0.5, 1e-3, 1e-9, 3e-16, 1e-17, 0.0])
+    for tol, Dmax in ((1e-16, 32), (1e-8, 32), (1e-16, 2)):
+        keep, lost = ops.truncation_rank(up(S), max(np.finfo(float).eps, tol), Dmax)
+        kref = min(int(np.sum(S > S[0] * max(np.finfo(float).eps, tol))), Dmax)
+        assert keep == kref and abs(lost - np.sqrt(np.sum(S[kref:] ** 2)) / S[0]) < 1e-15
+    rng = np.random.default_rng(1)
+    for scale in (1.0, 3e-7, 1e9, 0.99999, 2.0):
+        x = rng.standard_normal((13, 7)) * scale
+        t = up(x)
+        ops.pow2_scale_(t, ops.maxabs_bits(t))
+        assert np.array_equal(t.cpu().numpy(), x / ref_nfactor(x))
+    one = up(np.array([[3.7]]))
+    ops.pow2_scale_(one, ops.maxabs_bits(one))
+    assert one.item() == 1.0
+
+
+@pytest.mark.parametrize('conj', [True, False])
+@pytest.mark.parametrize('shape', [(1, 1, 1, 1, 16, 16), (3, 16, 5, 16, 16, 16), (8, 16, 8, 1, 16, 16), (4, 4, 6, 2, 3, 5)])
+def test_mpo_apply(conj, shape):
+    from tnac4o_b200 import ops
+    from oracle import RefMPS
+    Dl, dp, Dr, wl, wr, du = shape
+    rng = np.random.default_rng(sum(shape))
+    A = rng.standard_normal((Dl, dp, Dr))
+    W = rng.standard_normal((wl, dp, wr, du) if conj else (wl, du, wr, dp))
+    psi = RefMPS(1, d=1)
+    psi.A = [A.copy()]
+    psi.apply_mpo([W], conj=conj)
+    out = ops.mpo_apply(up(A), up(W), conj=conj).cpu().numpy()
+    assert out.shape == psi.A[0].shape
+    assert np.max(np.abs(out - psi.A[0])) < 1e-13 * dp
+
+
+@pytest.mark.parametrize('n', [1, 2, 100, 2048, 5000, 70000])
+def test_sort_keys(n):
+    from tnac4o_b200 import ops
+    from tnac4o_b200._native import Context, check, lib, ptr
+    rng = np.random.default_rng(n)
+    cap = ops.sort_capacity(n)
+    hi = rng.integers(0, 4, size=n, dtype=np.int64)
+    lo = rng.integers(0, 2 ** 62, size=n, dtype=np.int64) * rng.integers(0, 2, size=n)
+    tie = rng.permutation(n).astype(np.int64)
+    bufs = []
+    for a in (hi, lo, tie):
+        t = torch.zeros(cap, dtype=torch.int64, device=dev())
+        t[:n] = up(a)
+        bufs.append(t)
+    c = Context.get(dev())
+    check(lib.tn_sort_keys(c.handle, c.stream, ptr(bufs[0]), ptr(bufs[1]), ptr(bufs[2]), n))
+    got = np.stack([b[:n].cpu().numpy() for b in bufs], axis=1)
+    order = np.lexsort((tie, lo, hi))
+    assert np.array_equal(got, np.stack([hi, lo, tie], axis=1)[order])
+
+
+def test_energy_ising_kernel(J128):
+    import tnac4o_b200
+    from oracle.auxx_ref import energy_ising_dense
+    states = np.random.default_rng(0).integers(0, 2, size=(300, 128)).astype(np.int8)
+    E = tnac4o_b200.energy_Jij(J128, states)
+    assert np.max(np.abs(E - energy_ising_dense(J128, states))) < 1e-10

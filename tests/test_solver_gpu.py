@@ -1,0 +1,169 @@
+"""GPU parity tests of the phases and of the whole path against the oracle and the reference fixtures."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import SHAPES, droplet_couplings, droplet_golden, golden
+
+pytestmark = pytest.mark.gpu
+warnings.filterwarnings('ignore')
+
+
+def make(J, L=128, beta=3, rot=0, pre=False, cls=None):
+    import tnac4o_b200
+    from oracle import RefSolver
+    Nx, Ny = SHAPES[L]
+    ins = (cls or tnac4o_b200.tnac4o)(mode='Ising', Nx=Nx, Ny=Ny, Nc=8, J=J, beta=beta)
+    if rot:
+        ins.rotate_graph(rot)
+    if pre:
+        ins.precondition(mode='balancing')
+    return ins
+
+
+def upload_mps(ref_mps, dev):
+    """oracle MPS -> device MPS (used to test the search phase in isolation from the boundary-MPS phase)"""
+    from tnac4o_b200 import mps
+    psi = mps.MPS(d=1, L=ref_mps.L, Dmax=1, initial='X', device=dev)
+    psi.A = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in ref_mps.A]
+    psi.D = [psi.A[0].shape[0]] + [a.shape[2] for a in psi.A]
+    return psi
+
+
+@pytest.mark.parametrize('M,cut', [(64, 1e-8), (256, 1e-8), (1024, 0.0)])
+def test_search_phase_with_oracle_environments(J128, M, cut):
+    """same rhoT tensors on both sides: marginals to 1e-8 absolute, branch sets / energies / states exact"""
+    from oracle import RefSolver
+    ref = make(J128, cls=RefSolver)
+    trace = {}
+    ref.trace = lambda kind, **kw: trace.setdefault((kind, kw['ny'], kw['nx']), kw)
+    ref.search_ground_state(M=M, relative_P_cutoff=cut, Dmax=8)
+    ins = make(J128)
+    dev = ins._dev()
+    ins._setup_rhoT = lambda **kw: setattr(ins, 'rhoT', [upload_mps(p, dev) for p in ref.rhoT])
+    seen = {}
+    orig = ins._site_marginals
+
+    def spy(ws, br, RRat, ny, nx, want_P=False):
+        P = orig(ws, br, RRat, ny, nx, want_P=True)
+        seen[(ny, nx)] = (P.cpu().numpy(), br.vind[:br.n].cpu().numpy().copy())
+        return None
+    ins._site_marginals = spy
+    ins.search_ground_state(M=M, relative_P_cutoff=cut, Dmax=8)
+    for (ny, nx), (P, vind) in seen.items():
+        r = trace[('marginals', ny, nx)]
+        rows = {tuple(v): i for i, v in enumerate(r['vind'].view(np.uint8).tolist())}
+        idx = [rows[tuple(v)] for v in vind.tolist()]                    # same branch set, any order
+        assert len(idx) == len(rows)
+        assert np.max(np.abs(P - r['P'][idx])) <= 1e-8
+    assert ins.energy[0] == ref.energy[0]                                   # bit-exact (same table look-ups, same order)
+    assert np.array_equal(ins.states, ref.states)
+    assert int(ins.degeneracy) == int(ref.degeneracy)
+    np.testing.assert_allclose(ins.probability, ref.probability, rtol=1e-8)
+    np.testing.assert_allclose(ins.discarded_probability, ref.discarded_probability, rtol=1e-8)
+
+
+def test_boundary_mps_against_oracle(J128):
+    """gauge-invariant comparison of rhoT: normalised overlaps with the oracle's MPS, row by row"""
+    from oracle import RefSolver
+    ref = make(J128, cls=RefSolver)
+    ref._setup_rhoT(Dmax=8)
+    ins = make(J128)
+    ins._setup_rhoT(Dmax=8)
+    for ny in range(4):
+        a = [t.cpu().numpy() for t in ins.rhoT[ny].A]
+        b = ref.rhoT[ny].A
+
+        def ov(x, y):
+            E = np.ones((1, 1))
+            for p, q in zip(x, y):
+                E = np.einsum('ab,apc,bpd->cd', E, p, q)
+            return E.item()
+        assert abs(ov(a, b) / np.sqrt(ov(a, a) * ov(b, b)) - 1) < 1e-10
+        assert abs(ins.rhoT_overlap[ny] / ref.rhoT_overlap[ny] - 1) < 1e-8
+
+
+@pytest.mark.parametrize('rot,pre,D,M', [(0, False, 8, 256), (3, False, 8, 256), (0, False, 48, 1024), (0, True, 8, 256)])
+def test_ground_state_end_to_end(J128, rot, pre, D, M):
+    z = golden('ref_small.npz')
+    tag = 'gs_r%d_p%d_D%d_M%d' % (rot, pre, D, M)
+    ins = make(J128, rot=rot, pre=pre)
+    ins.search_ground_state(M=M, relative_P_cutoff=1e-8, Dmax=D)
+    assert abs(ins.energy[0] - z[tag + '_energy'][0]) < 1e-10
+    assert np.array_equal(ins.states, z[tag + '_states'])
+    assert np.array_equal(ins.binary_states(), z[tag + '_bits'])
+    assert int(ins.degeneracy) == int(z[tag + '_degeneracy'])
+    np.testing.assert_allclose(ins.probability, z[tag + '_probability'], rtol=1e-7)
+    e_file, bits_file = droplet_golden(128, 1)
+    assert abs(ins.energy[0] - e_file) < 1e-5 and np.array_equal(ins.binary_states()[0], bits_file)
+
+
+def test_marginals_end_to_end_against_reference_trace(J128):
+    """full GPU path (own rhoT) against the reference's marginals: max |dP| <= 1e-8 on normalised vectors"""
+    from oracle import RefSolver
+    ref = make(J128, cls=RefSolver)
+    trace = {}
+    ref.trace = lambda kind, **kw: trace.setdefault((kind, kw['ny'], kw['nx']), kw)
+    ref.search_ground_state(M=256, relative_P_cutoff=1e-8, Dmax=8)
+    ins = make(J128)
+    seen = {}
+    orig = ins._site_marginals
+
+    def spy(ws, br, RRat, ny, nx, want_P=False):
+        P = orig(ws, br, RRat, ny, nx, want_P=True)
+        seen[(ny, nx)] = (P.cpu().numpy(), br.vind[:br.n].cpu().numpy().copy())
+        return None
+    ins._site_marginals = spy
+    ins.search_ground_state(M=256, relative_P_cutoff=1e-8, Dmax=8)
+    worst = 0.0
+    for (ny, nx), (P, vind) in seen.items():
+        r = trace[('marginals', ny, nx)]
+        rows = {tuple(v): i for i, v in enumerate(r['vind'].view(np.uint8).tolist())}
+        common = [(i, rows[tuple(v)]) for i, v in enumerate(vind.tolist()) if tuple(v) in rows]
+        assert len(common) >= 0.99 * len(rows)                              # borderline members may differ
+        a, b = zip(*common)
+        worst = max(worst, np.max(np.abs(P[list(a)] - r['P'][list(b)])))
+    assert worst <= 1e-8
+    assert ins.energy[0] == ref.energy[0] and np.array_equal(ins.states, ref.states)
+
+
+def test_config2_L512(J128):
+    z = golden('ref_l512.npz')
+    ins = make(droplet_couplings(512), L=512)
+    ins.search_ground_state(M=2 ** 10, relative_P_cutoff=1e-8, Dmax=16)
+    assert abs(ins.energy[0] - z['gs_energy'][0]) < 1e-9
+    assert np.array_equal(ins.states, z['gs_states'])
+    e_file, bits_file = droplet_golden(512, 1)
+    assert abs(ins.energy[0] - e_file) < 1e-5 and np.array_equal(ins.binary_states()[0], bits_file)
+    np.testing.assert_allclose(ins.probability, z['gs_probability'], rtol=1e-6)
+
+
+def test_gibbs_sampling(J128):
+    import tnac4o_b200
+    z = golden('ref_small.npz')
+    ins = make(J128, beta=1)
+    np.random.seed(1)
+    ins.gibbs_sampling(M=128, Dmax=16)
+    assert ins.states.shape == (128, 16)
+    E = tnac4o_b200.energy_Jij(J128, ins.binary_states())
+    assert np.max(np.abs(E - ins.energy)) < 1e-6                            # examples/test_examples.py:56
+    same = np.all(ins.states == z['gibbs_states'], axis=1)
+    assert same.mean() >= 0.98                                              # identical draws up to 1e-9-level CDF ties
+    assert np.max(np.abs(ins.energy[same] - z['gibbs_energy'][same])) < 1e-10
+
+
+@pytest.mark.parametrize('rot', [0, 1])
+def test_spectrum_and_decode(J128, rot):
+    import tnac4o_b200
+    z = golden('ref_small.npz')
+    ins = make(J128, rot=rot)
+    ins.search_low_energy_spectrum(excitations_encoding=1, M=1024, relative_P_cutoff=1e-8, Dmax=16, max_dEng=1.0)
+    ins.decode_low_energy_states(max_dEng=1.0, max_states=2 ** 20)
+    assert len(ins.energy) == 31                                            # examples/test_examples.py:62
+    order = np.lexsort(ins.states.T[::-1])
+    assert np.array_equal(ins.states[order], z['sp_r%d_states' % rot])
+    np.testing.assert_allclose(ins.energy[order], z['sp_r%d_energy' % rot], atol=1e-10)
+    E = tnac4o_b200.energy_Jij(J128, ins.binary_states())
+    assert np.max(np.abs(E - ins.energy)) < 1e-4

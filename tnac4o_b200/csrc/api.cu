@@ -1,0 +1,85 @@
+// Context, error reporting and scratch management of the tnac4o_b200 C ABI.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void tn_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int tn_cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    tn_set_error("%s:%d: CUDA error %d (%s) in %s", file, line, (int)e, cudaGetErrorString(e), what);
+    return TN_ERR_CUDA;
+}
+
+void* tn_scratch(tn_ctx* ctx, int slot, size_t bytes) {
+    if (bytes <= ctx->scratch_bytes[slot]) return ctx->scratch[slot];
+    // grow-only; a grow synchronises the device so that no in-flight kernel still reads the old block
+    size_t want = bytes + bytes / 4 + (1 << 20);
+    cudaDeviceSynchronize();
+    if (ctx->scratch[slot]) cudaFree(ctx->scratch[slot]);
+    ctx->scratch[slot] = nullptr;
+    ctx->scratch_bytes[slot] = 0;
+    cudaError_t e = cudaMalloc(&ctx->scratch[slot], want);
+    if (e != cudaSuccess) {
+        tn_cuda_fail(e, "cudaMalloc(scratch)", __FILE__, __LINE__);
+        return nullptr;
+    }
+    ctx->scratch_bytes[slot] = want;
+    return ctx->scratch[slot];
+}
+
+extern "C" {
+
+int tn_version(void) { return 100; }
+
+const char* tn_last_error(void) { return g_err; }
+
+int tn_create(int device, tn_ctx** out) {
+    TN_REQUIRE(out != nullptr, "null output pointer");
+    int count = 0;
+    TN_CUDA(cudaGetDeviceCount(&count));
+    TN_REQUIRE(device >= 0 && device < count, "no such CUDA device");
+    TN_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    TN_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        tn_set_error("tnac4o_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+        return TN_ERR_ARG;
+    }
+    tn_ctx* ctx = new tn_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    cudaError_t e = cudaMallocHost(&ctx->pinned, 4096);
+    if (e != cudaSuccess) {
+        delete ctx;
+        return tn_cuda_fail(e, "cudaMallocHost", __FILE__, __LINE__);
+    }
+    if (!tn_scratch(ctx, TN_SLOT_GEMM, (size_t)32 << 20)) {
+        cudaFreeHost(ctx->pinned);
+        delete ctx;
+        return TN_ERR_NOMEM;
+    }
+    *out = ctx;
+    return TN_OK;
+}
+
+int tn_destroy(tn_ctx* ctx) {
+    if (!ctx) return TN_OK;
+    cudaSetDevice(ctx->device);
+    for (int i = 0; i < tn_ctx::SLOTS; ++i)
+        if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    delete ctx;
+    return TN_OK;
+}
+
+int64_t tn_launch_count(const tn_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,93 @@
+// Shared declarations of the tnac4o_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/tnac4o_b200.h"
+
+struct tn_ctx {
+    int device = 0;
+    int sm_count = 148;
+    static constexpr int SLOTS = 6;   // independent grow-only device scratch areas
+    void* scratch[SLOTS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_bytes[SLOTS] = {0, 0, 0, 0, 0, 0};
+    void* pinned = nullptr;           // small pinned host buffer for scalar read-backs
+    int64_t launches = 0;
+};
+
+void tn_set_error(const char* fmt, ...);
+int tn_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+enum { TN_SLOT_GEMM = 0, TN_SLOT_QR = 1, TN_SLOT_SVD = 2, TN_SLOT_SEARCH = 3, TN_SLOT_SORT = 4, TN_SLOT_MISC = 5 };
+void* tn_scratch(tn_ctx* ctx, int slot, size_t bytes);   // returns nullptr (and sets the error) on failure
+
+#define TN_CUDA(call)                                                          \
+    do {                                                                       \
+        cudaError_t e__ = (call);                                              \
+        if (e__ != cudaSuccess) return tn_cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define TN_LAUNCHED(ctx)                                                       \
+    do {                                                                       \
+        (ctx)->launches++;                                                     \
+        cudaError_t e__ = cudaGetLastError();                                  \
+        if (e__ != cudaSuccess) return tn_cuda_fail(e__, "kernel launch", __FILE__, __LINE__); \
+    } while (0)
+
+#define TN_REQUIRE(cond, msg)                                                  \
+    do {                                                                       \
+        if (!(cond)) {                                                         \
+            tn_set_error("%s:%d: %s (%s)", __FILE__, __LINE__, msg, #cond);    \
+            return TN_ERR_ARG;                                                 \
+        }                                                                      \
+    } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- device helpers ---------------------------------------------------------------------------
+// Order-preserving map double -> uint64 (total order on non-NaN values), used for atomicMax/Min.
+__host__ __device__ inline unsigned long long ordered_bits(double x) {
+    unsigned long long u;
+#ifdef __CUDA_ARCH__
+    u = (unsigned long long)__double_as_longlong(x);
+#else
+    memcpy(&u, &x, 8);
+#endif
+    return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+__host__ __device__ inline double from_ordered_bits(unsigned long long k) {
+    unsigned long long u = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)u);
+#else
+    double x;
+    memcpy(&x, &u, 8);
+    return x;
+#endif
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// 2^floor(log2 |x|) by exponent-field extraction, the rule of mps.nfactor (mps.py:83-85):
+// biased exponent e -> 2^(e-1023); e = 0 (zero / subnormal) gives 2^-1023.
+__device__ __forceinline__ double pow2_floor_from_bits(unsigned long long abs_bits) {
+    int e = (int)((abs_bits >> 52) & 0x7ff);
+    return ldexp(1.0, e - 1023);
+}
+#endif

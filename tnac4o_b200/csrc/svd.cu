@@ -1,0 +1,261 @@
+// Thin SVD by one-sided (Hestenes) Jacobi with block round-robin ordering -- replaces mps.svd / mps.svd_S
+// (mps.py:24-40, 62-73: LAPACK gesdd with gesvd fall-back).
+//
+// The matrix is held as "extended columns" E[k] = [ w_k (length a) | j_k (length ext) ]: w_k are the columns
+// being orthogonalised, j_k the accumulated rotations (identity at start, ext = 0 when only singular values
+// are wanted).  A CTA owns a pair of column blocks in shared memory, runs cyclic Jacobi among them with one
+// warp per column pair (dot products reduced with warp shuffles) and writes them back; block pairs follow a
+// round-robin tournament so that all pairs meet once per sweep.  Small problems are resident in one CTA and
+// iterate to convergence inside a single launch.  Rotations are computed from the 2x2 Gram of the two
+// columns, which keeps small singular values accurate to high relative precision; a Gram/eigh formulation of
+// the whole matrix is deliberately NOT used (hard part 1-iii).
+#include "common.cuh"
+
+namespace {
+
+constexpr int JT = 512;              // threads per CTA
+constexpr int JW = JT / 32;
+constexpr size_t SMEM_LIMIT = 200 * 1024;
+
+// E <- columns (or rows) of C, plus identity in the extension
+__global__ void jacobi_init_kernel(const double* __restrict__ C, int ldc, int m, int n, int transposed, double* E,
+                                   int ldw, int a, int ext, int nc) {
+    int64_t total = (int64_t)nc * ldw;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int k = (int)(i / ldw), e = (int)(i % ldw);
+        double v;
+        if (e < a) v = transposed ? C[(int64_t)k * ldc + e] : C[(int64_t)e * ldc + k];
+        else v = (e - a == k) ? 1.0 : 0.0;
+        E[i] = v;
+    }
+}
+
+// one tournament round over block pairs; CTA b handles the pair given by the circle method
+__global__ void __launch_bounds__(JT, 1)
+jacobi_round_kernel(double* __restrict__ E, int ldw, int a, int nc, int bsz, int nblocks, int round, int inner_max,
+                    double tol, unsigned int* rot_count) {
+    extern __shared__ __align__(16) double S[];      // [cols_here][ldw]
+    __shared__ int col_of[512];
+    __shared__ unsigned int sweep_rot;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int npe = nblocks + (nblocks & 1), n1 = npe - 1;
+    int b0, b1;
+    if (npe <= 2) { b0 = 0; b1 = 1; }
+    else {
+        int i = blockIdx.x;
+        b0 = (round + i) % n1;
+        b1 = (i == 0) ? n1 : (round + n1 - i) % n1;
+    }
+    if (b0 >= nblocks || b1 >= nblocks) return;      // partner is the phantom block of an odd tournament
+    int c0 = b0 * bsz, n0 = min(bsz, nc - c0);
+    int c1 = b1 * bsz, n1c = min(bsz, nc - c1);
+    const int ncol = n0 + n1c;
+    for (int i = tid; i < ncol; i += JT) col_of[i] = (i < n0) ? c0 + i : c1 + (i - n0);
+    __syncthreads();
+    for (int64_t i = tid; i < (int64_t)ncol * ldw; i += JT) {
+        int k = (int)(i / ldw), e = (int)(i % ldw);
+        S[i] = E[(int64_t)col_of[k] * ldw + e];
+    }
+    __syncthreads();
+
+    const int nce = ncol + (ncol & 1), r1 = nce - 1, half = nce / 2;
+    unsigned int my_rot_total = 0;
+    for (int sweep = 0; sweep < inner_max; ++sweep) {
+        if (tid == 0) sweep_rot = 0;
+        __syncthreads();
+        unsigned int my_rot = 0;
+        for (int r = 0; r < (nce > 1 ? r1 : 0); ++r) {
+            for (int i = warp; i < half; i += JW) {
+                int p = (nce == 2) ? 0 : (r + i) % r1;
+                int q = (i == 0) ? r1 : (r + r1 - i) % r1;
+                if (nce == 2) q = 1;
+                if (p >= ncol || q >= ncol) continue;
+                if (p > q) { int t = p; p = q; q = t; }
+                double* xp = S + (int64_t)p * ldw;
+                double* xq = S + (int64_t)q * ldw;
+                double app = 0.0, aqq = 0.0, apq = 0.0;
+                for (int e = lane; e < a; e += 32) {
+                    double u = xp[e], v = xq[e];
+                    app += u * u; aqq += v * v; apq += u * v;
+                }
+                app = warp_sum(app); aqq = warp_sum(aqq); apq = warp_sum(apq);
+                if (fabs(apq) > tol * sqrt(app) * sqrt(aqq) && app > 0.0 && aqq > 0.0) {
+                    double zeta = (aqq - app) / (2.0 * apq);
+                    double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+                    for (int e = lane; e < ldw; e += 32) {
+                        double u = xp[e], v = xq[e];
+                        xp[e] = cs * u - sn * v;
+                        xq[e] = sn * u + cs * v;
+                    }
+                    if (lane == 0) my_rot++;
+                }
+            }
+            __syncthreads();
+        }
+        if (lane == 0 && my_rot) atomicAdd(&sweep_rot, my_rot);
+        my_rot_total += my_rot;
+        __syncthreads();
+        unsigned int done = sweep_rot;
+        __syncthreads();
+        if (done == 0) break;
+    }
+    for (int64_t i = tid; i < (int64_t)ncol * ldw; i += JT) {
+        int k = (int)(i / ldw), e = (int)(i % ldw);
+        E[(int64_t)col_of[k] * ldw + e] = S[i];
+    }
+    if (lane == 0 && my_rot_total) atomicAdd(rot_count, my_rot_total);
+}
+
+// norms -> S (sorted descending), singular vectors with the sign rule of mps.svd (mps.py:35-39)
+__global__ void __launch_bounds__(JT, 1)
+jacobi_finish_kernel(const double* __restrict__ E, int ldw, int a, int ext, int nc, int transposed, double* __restrict__ U,
+                     int ldu, double* __restrict__ Sout, double* __restrict__ Vt, int ldvt, double* sv_tmp, int* rank_tmp) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int k = warp; k < nc; k += JW) {
+        const double* w = E + (int64_t)k * ldw;
+        // scaled 2-norm is unnecessary: entries are normalised to O(1) by nfactor before every SVD
+        double s = 0.0;
+        for (int e = lane; e < a; e += 32) s += w[e] * w[e];
+        s = warp_sum(s);
+        if (lane == 0) sv_tmp[k] = sqrt(s);
+    }
+    __syncthreads();
+    for (int k = tid; k < nc; k += JT) {
+        double sk = sv_tmp[k];
+        int r = 0;
+        for (int j = 0; j < nc; ++j) {
+            double sj = sv_tmp[j];
+            r += (sj > sk) || (sj == sk && j < k);
+        }
+        rank_tmp[k] = r;
+        Sout[r] = sk;
+    }
+    __syncthreads();
+    if (ext == 0) return;
+    for (int k = warp; k < nc; k += JW) {
+        const double* w = E + (int64_t)k * ldw;
+        const double* jv = w + a;
+        const double sk = sv_tmp[k];
+        const double inv = (sk > 0.0) ? 1.0 / sk : 0.0;
+        const int r = rank_tmp[k];
+        double mxw = -INFINITY, mnw = INFINITY, mxj = -INFINITY, mnj = INFINITY;
+        for (int e = lane; e < a; e += 32) { double v = w[e] * inv; mxw = fmax(mxw, v); mnw = fmin(mnw, v); }
+        for (int e = lane; e < ext; e += 32) { double v = jv[e]; mxj = fmax(mxj, v); mnj = fmin(mnj, v); }
+        mxw = warp_max(mxw); mnw = warp_min(mnw); mxj = warp_max(mxj); mnj = warp_min(mnj);
+        const double sg = ((fabs(mnw) > mxw) && (fabs(mnj) > mxj)) ? -1.0 : 1.0;
+        if (!transposed) {
+            for (int e = lane; e < a; e += 32) U[(int64_t)e * ldu + r] = sg * w[e] * inv;      // a = m
+            for (int e = lane; e < ext; e += 32) Vt[(int64_t)r * ldvt + e] = sg * jv[e];        // ext = n
+        } else {
+            for (int e = lane; e < ext; e += 32) U[(int64_t)e * ldu + r] = sg * jv[e];          // ext = m
+            for (int e = lane; e < a; e += 32) Vt[(int64_t)r * ldvt + e] = sg * w[e] * inv;     // a = n
+        }
+    }
+}
+
+__global__ void truncation_rank_kernel(const double* __restrict__ S, int k, double tol, int Dmax, int* keep_out,
+                                       double* disc_out) {
+    // single warp; k is at most a few thousand
+    int lane = threadIdx.x;
+    double s0 = S[0];
+    int cnt = 0;
+    for (int i = lane; i < k; i += 32) cnt += (S[i] > s0 * tol);
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    int keep = min(cnt, Dmax);
+    double ss = 0.0;
+    for (int i = keep + lane; i < k; i += 32) ss += S[i] * S[i];
+    ss = warp_sum(ss);
+    if (lane == 0) { *keep_out = keep; *disc_out = sqrt(ss) / s0; }
+}
+
+}  // namespace
+
+extern "C" int tn_svd(tn_ctx* ctx, void* stream, int m, int n, const double* C, int ldc, double* U, int ldu, double* S,
+                      double* Vt, int ldvt, int want_vectors, int* h_sweeps) {
+    TN_REQUIRE(ctx != nullptr, "null context");
+    TN_REQUIRE(m >= 1 && n >= 1, "empty matrix");
+    cudaStream_t st = as_stream(stream);
+    const int transposed = (m < n);
+    const int a = transposed ? n : m;
+    const int nc = transposed ? m : n;
+    const int ext = want_vectors ? nc : 0;
+    const int ldw = a + ext;
+    TN_REQUIRE(nc <= 4096, "matrix too large for the Jacobi SVD");
+    TN_REQUIRE((size_t)2 * ldw * sizeof(double) <= SMEM_LIMIT, "column too long for the shared-memory Jacobi kernel");
+
+    size_t bytes = (size_t)nc * ldw * sizeof(double) + (size_t)nc * (sizeof(double) + sizeof(int)) + 64;
+    char* ws = (char*)tn_scratch(ctx, TN_SLOT_SVD, bytes);
+    if (!ws) return TN_ERR_NOMEM;
+    double* E = (double*)ws;
+    double* sv_tmp = E + (size_t)nc * ldw;
+    int* rank_tmp = (int*)(sv_tmp + nc);
+    unsigned int* rot = (unsigned int*)(rank_tmp + nc + (nc & 1));
+
+    {
+        int64_t total = (int64_t)nc * ldw;
+        int blocks = (int)((total + 255) / 256 < 8 * ctx->sm_count ? (total + 255) / 256 : 8 * ctx->sm_count);
+        jacobi_init_kernel<<<blocks, 256, 0, st>>>(C, ldc, m, n, transposed, E, ldw, a, ext, nc);
+        TN_LAUNCHED(ctx);
+    }
+    int cmax = (int)(SMEM_LIMIT / ((size_t)ldw * sizeof(double)));
+    cmax -= (cmax & 1);
+    if (cmax > 512) cmax = 512;
+    const double tol = sqrt((double)a) * 2.220446049250313e-16;
+    int sweeps = 0;
+    unsigned int* h_rot = (unsigned int*)ctx->pinned;
+    TN_CUDA(cudaFuncSetAttribute(jacobi_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+    if (nc <= cmax) {
+        // resident: one CTA iterates to convergence
+        int bsz = (nc + 1) / 2, nblocks = (nc > bsz) ? 2 : 1;
+        size_t smem = (size_t)nc * ldw * sizeof(double);
+        TN_CUDA(cudaMemsetAsync(rot, 0, sizeof(unsigned int), st));
+        if (nc > 1) {
+            jacobi_round_kernel<<<1, JT, smem, st>>>(E, ldw, a, nc, bsz, nblocks, 0, 60, tol, rot);
+            TN_LAUNCHED(ctx);
+        }
+        sweeps = 1;
+    } else {
+        int bsz = cmax / 2, nblocks = ceil_div(nc, bsz);
+        int npe = nblocks + (nblocks & 1);
+        size_t smem = (size_t)2 * bsz * ldw * sizeof(double);
+        bool converged = false;
+        for (sweeps = 0; sweeps < 60 && !converged;) {
+            TN_CUDA(cudaMemsetAsync(rot, 0, sizeof(unsigned int), st));
+            for (int r = 0; r < npe - 1; ++r) {
+                jacobi_round_kernel<<<npe / 2, JT, smem, st>>>(E, ldw, a, nc, bsz, nblocks, r, 2, tol, rot);
+                TN_LAUNCHED(ctx);
+            }
+            ++sweeps;
+            TN_CUDA(cudaMemcpyAsync(h_rot, rot, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+            TN_CUDA(cudaStreamSynchronize(st));
+            converged = (*h_rot == 0);
+        }
+        if (!converged) {
+            tn_set_error("Jacobi SVD of a %d x %d matrix did not converge in %d sweeps", m, n, sweeps);
+            return TN_ERR_NOCONV;
+        }
+    }
+    jacobi_finish_kernel<<<1, JT, 0, st>>>(E, ldw, a, ext, nc, transposed, U, ldu, S, Vt, ldvt, sv_tmp, rank_tmp);
+    TN_LAUNCHED(ctx);
+    if (h_sweeps) *h_sweeps = sweeps;
+    return TN_OK;
+}
+
+extern "C" int tn_truncation_rank(tn_ctx* ctx, void* stream, const double* S, int k, double tol, int Dmax, int* h_keep,
+                                  double* h_discarded) {
+    TN_REQUIRE(ctx != nullptr && k >= 1, "bad arguments");
+    cudaStream_t st = as_stream(stream);
+    char* ws = (char*)tn_scratch(ctx, TN_SLOT_MISC, 64);
+    if (!ws) return TN_ERR_NOMEM;
+    int* d_keep = (int*)ws;
+    double* d_disc = (double*)(ws + 8);
+    truncation_rank_kernel<<<1, 32, 0, st>>>(S, k, tol, Dmax, d_keep, d_disc);
+    TN_LAUNCHED(ctx);
+    char* hp = (char*)ctx->pinned + 64;
+    TN_CUDA(cudaMemcpyAsync(hp, ws, 16, cudaMemcpyDeviceToHost, st));
+    TN_CUDA(cudaStreamSynchronize(st));
+    *h_keep = *(int*)hp;
+    *h_discarded = *(double*)(hp + 8);
+    return TN_OK;
+}

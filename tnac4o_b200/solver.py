@@ -1,0 +1,753 @@
+"""The solver object: the reference's ``tnac4o(mode, Nx, Ny, Nc, J, beta)`` API on top of the sm_100a kernels.
+
+Drop-in for /root/reference/tnac4o/tnac4o.py on the contraction path: same constructor, same entry points
+(``search_ground_state``, ``gibbs_sampling`` = ``sample``, ``search_low_energy_spectrum``,
+``decode_low_energy_states``, ``precondition``, ``rotate_graph``, ``save`` / ``load``, ``binary_states``), same
+result attributes and dtypes.  Host code prepares O(L) tables and steers the row / site loop; every
+per-branch quantity lives in HBM and is produced by kernels of libtnac4o_b200.so.  There is no CPU fallback.
+"""
+import ctypes
+import logging
+import time
+
+import numpy as np
+import scipy.linalg
+import scipy.sparse
+import torch
+
+from . import mps, ops
+from ._native import Context, check, lib, ptr
+from .model import IsingLattice, SiteTables, cell_bits, upper_triangular
+
+F64 = torch.float64
+_NEG_INF_BITS = 0x000FFFFFFFFFFFFF          # order-preserving encoding of -inf (common.cuh: ordered_bits)
+
+
+def _decode_ordered(bits):
+    bits = int(bits) & 0xFFFFFFFFFFFFFFFF
+    raw = (bits & 0x7FFFFFFFFFFFFFFF) if (bits >> 63) else (~bits & 0xFFFFFFFFFFFFFFFF)
+    return float(np.array([raw], dtype=np.uint64).view(np.float64)[0])
+
+
+def load(file_name):
+    """Load a solution saved with :meth:`tnac4o.save` (tnac4o.py:31-75); couplings are not part of the file."""
+    d = np.load(file_name, allow_pickle=True).item()
+    ins = tnac4o(mode=d.get('mode'), Nx=d.get('Nx'), Ny=d.get('Ny'), Nc=d.get('Nc'), beta=d.get('beta'))
+    for key in ('energy', 'probability', 'degeneracy', 'states', 'discarded_probability', 'negative_probability'):
+        setattr(ins, key, d.get(key))
+    ins.ind0 = d.get('ind')
+    ins.adj = np.zeros((0, 0))
+    if d.get('excitations_encoding') is not None:
+        ins.excitations_encoding = d.get('excitations_encoding')
+        ins.d, ins.invd, ins.el, ins.free_d = d.get('d'), d.get('invd'), d.get('el'), d.get('free_d')
+    return ins
+
+
+class tnac4o:
+    r"""Tensor-network solver for Ising problems on a quasi-2d lattice (see the reference docstring,
+    tnac4o.py:78-143).  ``mode='Ising'``; spin index :math:`i = k N_x N_c + l N_c + m`."""
+
+    def __init__(self, mode='Ising', Nx=4, Ny=4, Nc=8, beta=1, J=None, device=None):
+        if mode != 'Ising':
+            raise NotImplementedError("tnac4o_b200 implements mode='Ising' (RMF is outside the hot path, SURVEY.md section 2 row 24)")
+        if Nc > 8:
+            raise ValueError('Single cluster is too large (cell states are stored as one byte: Nc <= 8).')
+        self.mode, self.beta = mode, beta
+        self.Nx_model, self.Ny_model = Nx, Ny
+        self.Nx, self.Ny, self.Nc = Nx, Ny, Nc
+        self.indtype = np.int8
+        self.L = Nx * Ny * Nc
+        self.order = np.arange(Nx * Ny)
+        self.order_i = np.arange(Nx * Ny)
+        self.logger = logging.getLogger('tnac4o')
+        self.energy, self.probability = np.zeros(0), np.zeros(0)
+        self.rotation, self.degeneracy = 0, 0
+        self.states = np.zeros((0, Nx * Ny), dtype=self.indtype)
+        self.discarded_probability, self.negative_probability = -np.inf, 0.
+        self.device = None if device is None else torch.device(device)
+        self.stats = {}
+        self._sites = None
+        if J is not None:
+            self.J = upper_triangular(J, self.L)
+            self.J0 = self.J.copy()
+            self._divide_couplings()
+            self.ind0 = [[self.lat.ind[ny][nx] for nx in range(Nx)] for ny in range(Ny)]
+            self.active = int(sum(len(a) for row in self.ind0 for a in row))
+
+    # ------------------------------------------------------------------ model preparation (host)
+    def _divide_couplings(self):
+        """tnac4o.py:1391-1457"""
+        self.lat = IsingLattice(self.J, self.Nx, self.Ny, self.Nc)
+        for name in ('ind', 'N', 'sN', 'sl', 'sd', 'sr', 'su', 'lr', 'ld', 'id', 'ir', 'Jin', 'Jl', 'Ju'):
+            setattr(self, name, getattr(self.lat, name))
+        self._reset_X()
+
+    def _reset_X(self):
+        """identity gauges (tnac4o.py:1811-1820)"""
+        Ny, Nx = self.Ny, self.Nx
+        self.Xu = np.ones((Ny, Nx, np.max(self.ld)))
+        self.Xd = np.ones((Ny, Nx, np.max(self.ld)))
+        self.Xl = np.ones((Ny, Nx, np.max(self.lr)))
+        self.Xr = np.ones((Ny, Nx, np.max(self.lr)))
+        self.overlaps_ud = np.empty(shape=[0, Ny - 1])
+        self._sites = None
+
+    def rotate_graph(self, rot=1):
+        """quarter turns of the lattice, cumulative (tnac4o.py:290-340)"""
+        for _ in range(rot):
+            self.rotation += 1
+            Nx, Ny, Nc = self.Nx, self.Ny, self.Nc
+            spin_map = np.arange(self.L)
+            order = np.arange(Nx * Ny)
+            order_i = np.arange(Nx * Ny)
+            for nx in range(Nx):
+                for ny in range(Ny):
+                    src = (ny * Nx + nx) * Nc + np.arange(Nc)
+                    dst = ((Nx - nx - 1) * Ny + ny) * Nc + np.arange(Nc)
+                    spin_map[src] = dst
+                    a, b = ny * Nx + nx, (Nx - nx - 1) * Ny + ny
+                    order[a], order_i[b] = b, a
+            self.Nx, self.Ny = Ny, Nx
+            self.J = self.J[spin_map, :][:, spin_map]
+            self.J = scipy.sparse.triu(self.J) + scipy.sparse.tril(self.J, -1).T
+            self.order = order_i[self.order]
+        self.order_i[self.order] = np.arange(self.Nx * self.Ny)
+        self.rotation = np.mod(self.rotation, 4)
+        self._divide_couplings()
+
+    def add_noise(self, amplitude=1e-7):
+        """tnac4o.py:917-933 (consumes the global numpy RNG like the reference)"""
+        self.logger.info('Adding noise to the coupling with ampliture %.2e', amplitude)
+        nzr = self.J.nonzero()
+        kk = ((np.random.rand(len(nzr[0])) * 2 - 1) * amplitude)
+        self.J = scipy.sparse.lil_matrix(self.J)
+        for i, j, k in zip(nzr[0], nzr[1], kk):
+            self.J[i, j] += k
+        self.J = scipy.sparse.csr_matrix(self.J)
+        self._divide_couplings()
+
+    # ------------------------------------------------------------------ device tables
+    def _dev(self):
+        if self.device is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError('tnac4o_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+            self.device = torch.device('cuda', torch.cuda.current_device())
+        return self.device
+
+    def _upload_sites(self):
+        dev = self._dev()
+        X = (self.Xu, self.Xl, self.Xr, self.Xd)
+        self._sites = [[SiteTables(self.lat, ny, nx, self.beta, X, dev) for nx in range(self.Nx)] for ny in range(self.Ny)]
+        self._sites_beta = self.beta
+        return self._sites
+
+    def _site_tables(self):
+        if self._sites is None or self._sites_beta != self.beta:
+            self._upload_sites()
+        return self._sites
+
+    # ------------------------------------------------------------------ boundary MPS
+    def _row_mpo(self, ny):
+        sites = self._site_tables()
+        At = mps.MPO(L=self.Nx)
+        for nx in range(self.Nx):
+            At.set_direct(sites[ny][nx].Wmpo, nx)
+        return At
+
+    def _setup_rhoT(self, graduate_truncation=True, Dmax=32, tolS=1e-16, tolV=1e-10, max_sweeps=20):
+        """boundary MPS of rows ny..Ny-1 for every ny, from the top (tnac4o.py:1674-1695)"""
+        dev = self._dev()
+        self.rhoT = [None] * (self.Ny + 1)
+        self.rhoT_overlap = [1] * (self.Ny + 1)
+        self.rhoT_discarded = [0] * (self.Ny + 1)
+        self.rhoT[-1] = mps.MPS(d=1, L=self.Nx, Dmax=1, initial='X', device=dev)
+        for ny in range(self.Ny - 1, -1, -1):
+            psi = self.rhoT[ny + 1].copy()
+            psi.apply_mpo(self._row_mpo(ny), Hconj=True)
+            self.rhoT_overlap[ny] = psi.compress_mps(Dmax=Dmax, tolS=tolS, tolV=tolV, max_sweeps=max_sweeps,
+                                                     graduate_truncation=graduate_truncation, verbose=False)
+            self.rhoT_discarded[ny] = max(psi.discarded)
+            self.rhoT[ny] = psi
+
+    def _setup_rhoB(self, graduate_truncation=True, Dmax=32, tolS=1e-16, tolV=1e-10, max_sweeps=20):
+        """the same from the bottom (tnac4o.py:1697-1718); used by the preconditioning only"""
+        dev = self._dev()
+        self.rhoB = [None] * (self.Ny + 1)
+        self.rhoB[0] = mps.MPS(d=1, L=self.Nx, Dmax=1, initial='X', device=dev)
+        for ny in range(self.Ny):
+            psi = self.rhoB[ny].copy()
+            psi.apply_mpo(self._row_mpo(ny), Hconj=False)
+            psi.compress_mps(Dmax=Dmax, tolS=tolS, tolV=tolV, max_sweeps=max_sweeps,
+                             graduate_truncation=graduate_truncation, verbose=False)
+            self.rhoB[ny + 1] = psi
+
+    # ------------------------------------------------------------------ preconditioning
+    def precondition(self, mode='balancing', steps=2, beta_cond=[], Dmax_cond=[], max_scale=1024,
+                     graduate_truncation=False, tolS=1e-16, tolV=1e-10, max_sweeps=20):
+        """balancing heuristic on the vertical bonds (tnac4o.py:342-379)"""
+        if mode != 'balancing':
+            return
+        if not beta_cond:
+            beta_cond = [self.beta * 2. ** (nn - steps) for nn in range(steps)]
+        if not Dmax_cond:
+            Dmax_cond = [8] * len(beta_cond)
+        main_beta = self.beta
+        for b, D in zip(beta_cond, Dmax_cond):
+            self.beta = b
+            self.logger.info('Preconditioning with beta = %.2f', self.beta)
+            keep_time = time.time()
+            self._update_conditioning(direction='ud', Dmax=D, graduate_truncation=graduate_truncation, tolS=tolS,
+                                      tolV=tolV, max_sweeps=max_sweeps, max_scale=max_scale)
+            self.logger.info('Elapsed: %.2f seconds', time.time() - keep_time)
+        self.beta = main_beta
+        self._sites = None
+
+    def _update_conditioning(self, direction='ud', graduate_truncation=False, Dmax=8, tolS=1e-16, tolV=1e-10,
+                             max_sweeps=4, max_scale=1024):
+        """tnac4o.py:1824-1918.  Bond environments (a few 16 x 16 matrices) are balanced on the host with the same
+        LAPACK routine as the reference (dgebal through scipy); all MPS work runs on the device."""
+        if direction != 'ud':
+            raise NotImplementedError("only direction='ud' is reachable in the reference (tnac4o.py:374-377)")
+        cap = 2.0 ** np.floor(np.log2(np.sqrt(max_scale)))
+        self._sites = None
+        self._setup_rhoT(graduate_truncation, Dmax, tolS, tolV, max_sweeps)
+        self._setup_rhoB(graduate_truncation, Dmax, tolS, tolV, max_sweeps)
+        Nx = self.Nx
+        overlaps = np.ones((2, self.Ny - 1))
+
+        def fro(t):
+            return float(torch.linalg.vector_norm(t).item())
+
+        def normalise_(t):
+            t *= 1.0 / fro(t)
+
+        for ny in range(1, self.Ny):
+            bot, top = self.rhoB[ny], self.rhoT[ny]
+            for nx in range(Nx):
+                bot.update_RL_mix(top, nx)
+                normalise_(bot.R[nx + 1])
+
+            def rebalance(nx):
+                env = bot.bond_env_mix(top, nx).cpu().numpy()
+                _, scale = scipy.linalg.matrix_balance(env, permute=False, separate=True)
+                scale = np.minimum(np.maximum(scale[0], 1 / cap), cap)
+                o1 = float(bot.expectation_mix(top, nx).item()) / (fro(bot.A[nx]) * fro(top.A[nx]))
+                bot.apply_diagonalO(scale, nx)
+                top.apply_diagonalO(1 / scale, nx)
+                o2 = float(bot.expectation_mix(top, nx).item()) / (fro(bot.A[nx]) * fro(top.A[nx]))
+                if o1 < overlaps[0, ny - 1]:
+                    overlaps[0, ny - 1] = o1
+                    overlaps[1, ny - 1] = max(o1, o2)
+                width = self.ld[ny - 1, nx]
+                self.Xd[ny - 1, nx, :width] *= scale
+                self.Xu[ny, nx, :width] *= 1 / scale
+
+            for nx in range(Nx - 1, -1, -1):
+                rebalance(nx)
+                if nx > 0:
+                    bot.orth_right(nx)
+                    bot.attach_AC()
+                    top.orth_right(nx)
+                    top.attach_AC()
+                    bot.update_RR_mix(top, nx)
+                    normalise_(bot.R[nx])
+            for nx in range(Nx):
+                rebalance(nx)
+                if nx < Nx - 1:
+                    bot.orth_left(nx)
+                    bot.attach_CA()
+                    top.orth_left(nx)
+                    top.attach_CA()
+                    bot.update_RL_mix(top, nx)
+                    normalise_(bot.R[nx + 1])
+        self.overlaps_ud = np.vstack([self.overlaps_ud, overlaps])
+        self.rhoB = []
+        self._sites = None
+
+    # ------------------------------------------------------------------ search machinery
+    def _key_offsets(self, ny, nx):
+        """bit offsets of the Nx+1 boundary indices inside the 128-bit merge key after site (ny, nx)"""
+        widths = []
+        for j in range(self.Nx + 1):
+            if j <= nx:
+                w = self.sd[ny][j]
+            elif j == nx + 1:
+                w = self.sr[ny][nx]
+            else:
+                w = self.su[ny][j - 1]
+            widths.append(int(w))
+        offs = np.concatenate(([0], np.cumsum(widths)[:-1])).astype(np.uint8)
+        if sum(widths) > 128:
+            raise ValueError('boundary index row needs %d bits; the merge key holds 128' % sum(widths))
+        return offs
+
+    class _Branches:
+        """device arrays of the live partial configurations"""
+
+        def __init__(self, cap, Nx, nsites, Dcap, dev):
+            self.vind = torch.zeros((cap, Nx + 1), dtype=torch.uint8, device=dev)
+            self.states = torch.zeros((cap, nsites), dtype=torch.uint8, device=dev)
+            self.root = torch.zeros(cap, dtype=torch.int32, device=dev)
+            self.Eng = torch.zeros(cap, dtype=F64, device=dev)
+            self.prob = torch.zeros(cap, dtype=F64, device=dev)
+            self.deg = torch.ones(cap, dtype=torch.int64, device=dev)
+            self.RL = torch.ones((cap * Dcap,), dtype=F64, device=dev)
+            self.n = 1
+
+    def _alloc_search(self, cap, nsmax, Dcap):
+        dev = self._dev()
+        nsites = self.Nx * self.Ny
+        ws = {}
+        ws['cur'] = self._Branches(cap, self.Nx, nsites, Dcap, dev)
+        ws['nxt'] = self._Branches(cap, self.Nx, nsites, Dcap, dev)
+        ncand = cap * nsmax
+        kcap = ops.sort_capacity(ncand)
+        ws['cand'] = torch.empty(ncand, dtype=F64, device=dev)
+        ws['flag'] = torch.empty(cap, dtype=F64, device=dev)
+        ws['surv'] = torch.empty(ncand, dtype=torch.int32, device=dev)
+        for name in ('khi', 'klo', 'ktie'):
+            ws[name] = torch.empty(kcap, dtype=torch.int64, device=dev)
+        for name in ('parent', 'cell', 'g_rep', 'g_start', 'g_size', 'sel'):
+            ws[name] = torch.empty(ncand, dtype=torch.int32, device=dev)
+        for name in ('Enew', 'Pnew', 'g_prob', 'g_E'):
+            ws[name] = torch.empty(ncand, dtype=F64, device=dev)
+        ws['g_deg'] = torch.empty(ncand, dtype=torch.int64, device=dev)
+        ws['count'] = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws['maxbits'] = torch.zeros(1, dtype=torch.int64, device=dev)
+        ws['pdbits'] = torch.full((1,), _NEG_INF_BITS, dtype=torch.int64, device=dev)
+        ws['gmin'] = torch.zeros(1, dtype=F64, device=dev)
+        return ws
+
+    def _setup_RR(self, br, ny):
+        """right environments of row ny for every row-start branch, all levels (tnac4o.py:1768-1784).
+        RRat[nx] covers sites nx..Nx-1; site nx of the search uses RRat[nx + 1]."""
+        dev = self._dev()
+        c = Context.get(dev)
+        sites = self._site_tables()[ny]
+        A = self.rhoT[ny + 1].A
+        nb = br.n
+        RRat = [None] * (self.Nx + 1)
+        RRat[self.Nx] = torch.ones((nb, 1, 1), dtype=F64, device=dev)
+        for nx in range(self.Nx - 1, 0, -1):
+            Dl, nd, Dr = A[nx].shape
+            out = torch.empty((nb, Dl, sites[nx].nl), dtype=F64, device=dev)
+            up = br.vind[:, nx + 1:]
+            check(lib.tn_rr_level(c.handle, c.stream, sites[nx].ref, nb, Dl, Dr, ptr(A[nx]), ptr(RRat[nx + 1]),
+                                  up.data_ptr(), br.vind.stride(0), ptr(out)))
+            RRat[nx] = out
+        br.root[:nb] = torch.arange(nb, dtype=torch.int32, device=dev)
+        return RRat
+
+    def _site_marginals(self, ws, br, RRat, ny, nx, want_P=False):
+        """T1 = RL . A on the DMMA path, then the fused marginal kernel; returns (Dl, nd, Dr) and optional P"""
+        dev = self._dev()
+        c = Context.get(dev)
+        site = self._site_tables()[ny][nx]
+        A = self.rhoT[ny + 1].A[nx]
+        Dl, nd, Dr = A.shape
+        B = br.n
+        T1 = ops.gemm(br.RL[:B * Dl].view(B, Dl), A.view(Dl, nd * Dr))
+        P = torch.empty((B, site.nS), dtype=F64, device=dev) if want_P else None
+        cand = None if want_P == 'only' else ws['cand']
+        check(lib.tn_marginals(c.handle, c.stream, site.ref, B, Dr, ptr(T1), ptr(RRat[nx + 1]), ptr(br.root), ptr(br.vind),
+                               br.vind.stride(0), nx, ptr(br.prob) if cand is not None else None, ptr(cand), ptr(ws['flag']),
+                               ptr(ws['maxbits']) if cand is not None else None, ptr(P)))
+        ws['gmin'] = torch.minimum(ws['gmin'], ws['flag'][:B].min())
+        self.stats['marginals'] = self.stats.get('marginals', 0) + B
+        return P
+
+    def _site_step(self, ws, RRat, ny, nx, M, relative_P_cutoff, min_dEng):
+        """one site of the branch-and-bound: select -> expand -> merge -> top-M -> materialise (tnac4o.py:456-535)"""
+        dev = self._dev()
+        c = Context.get(dev)
+        br, nxt = ws['cur'], ws['nxt']
+        site = self._site_tables()[ny][nx]
+        A = self.rhoT[ny + 1].A[nx]
+        Dl, nd, Dr = A.shape
+        B = br.n
+        ncand = B * site.nS
+        K = ctypes.c_int(0)
+        check(lib.tn_select(c.handle, c.stream, ptr(ws['cand']), ncand, ptr(ws['maxbits']), float(relative_P_cutoff),
+                            ptr(ws['surv']), ptr(ws['count']), ptr(ws['pdbits']), ctypes.byref(K)))
+        K = K.value
+        offs = self._key_offsets(ny, nx)
+        check(lib.tn_expand(c.handle, c.stream, site.ref, K, nx, int(nx > 0), int(ny > 0), self.Nx + 1,
+                            offs.ctypes.data_as(ctypes.c_void_p), ptr(ws['surv']), ptr(br.vind), br.vind.stride(0),
+                            ptr(br.Eng), ptr(ws['cand']), ptr(ws['khi']), ptr(ws['klo']), ptr(ws['ktie']), ptr(ws['parent']),
+                            ptr(ws['cell']), ptr(ws['Enew']), ptr(ws['Pnew'])))
+        G = ctypes.c_int(0)
+        check(lib.tn_merge(c.handle, c.stream, K, ptr(ws['khi']), ptr(ws['klo']), ptr(ws['ktie']), ptr(ws['Enew']),
+                           ptr(ws['Pnew']), ptr(ws['parent']), ptr(br.deg), float(min_dEng), ptr(ws['g_rep']),
+                           ptr(ws['g_deg']), ptr(ws['g_prob']), ptr(ws['g_E']), ptr(ws['g_start']), ptr(ws['g_size']),
+                           ctypes.byref(G)))
+        G = G.value
+        groups = None
+        if ws.get('want_groups'):
+            # member lists in sorted order are needed by the droplet pass before the key arrays are reused
+            groups = {'order': (ws['ktie'][:K] & 0xFFFFFFFF).to(torch.int32).cpu().numpy(), 'K': K, 'G': G}
+        check(lib.tn_topm(c.handle, c.stream, G, M, ptr(ws['g_prob']), ptr(ws['khi']), ptr(ws['klo']), ptr(ws['ktie']),
+                          ptr(ws['sel']), ptr(ws['pdbits'])))
+        Bn = min(G, M)
+        check(lib.tn_materialise(c.handle, c.stream, site.ref, Bn, nx, ny * self.Nx + nx, self.Nx * self.Ny,
+                                 br.vind.stride(0), Dl, Dr, ptr(ws['sel']), ptr(ws['g_rep']), ptr(ws['g_deg']),
+                                 ptr(ws['g_prob']), ptr(ws['parent']), ptr(ws['cell']), ptr(ws['Enew']), ptr(br.vind),
+                                 ptr(br.states), ptr(br.root), ptr(br.RL), ptr(A), ptr(nxt.vind), ptr(nxt.states),
+                                 ptr(nxt.root), ptr(nxt.Eng), ptr(nxt.prob), ptr(nxt.deg), ptr(nxt.RL)))
+        nxt.n = Bn
+        ws['cur'], ws['nxt'] = nxt, br
+        self.stats['candidates_kept'] = self.stats.get('candidates_kept', 0) + K
+        return groups
+
+    def _max_bond(self):
+        return max(max(psi.D) for psi in self.rhoT)
+
+    def _finish_search(self, ws, t_rho, t0):
+        br = ws['cur']
+        n = br.n
+        torch.cuda.synchronize(self._dev())
+        self.stats['seconds_rhoT'] = t_rho
+        self.stats['seconds_search'] = time.time() - t0
+        self.energy = br.Eng[:n].cpu().numpy()
+        self.degeneracy = int(br.deg[0].item())
+        states = br.states[:n].cpu().numpy().view(np.int8)
+        self.states = states[:, self.order]
+        self.probability = br.prob[:n].cpu().numpy()
+        self.discarded_probability = _decode_ordered(ws['pdbits'].item())
+        self.negative_probability = min(float(ws['gmin'].item()), 0)
+
+    def search_ground_state(self, M=2 ** 10, relative_P_cutoff=1e-6, min_dEng=1e-12, graduate_truncation=True,
+                            Dmax=32, tolS=1e-16, tolV=1e-10, max_sweeps=20):
+        """Branch-and-bound search for the most probable state (tnac4o.py:381-551).  Returns the energies."""
+        dev = self._dev()
+        c = Context.get(dev)
+        t0 = time.time()
+        self.stats = {}
+        self.logger.info('Searching ground state with beta = %.2f', self.beta)
+        self.logger.info('Preprocesing ... ')
+        self._setup_rhoT(graduate_truncation=graduate_truncation, Dmax=Dmax, tolS=tolS, tolV=tolV, max_sweeps=max_sweeps)
+        torch.cuda.synchronize(dev)
+        t_rho = time.time() - t0
+        self.logger.info('Elapsed: %.2f seconds', t_rho)
+        t0 = time.time()
+        ws = self._alloc_search(M, int(np.max(self.N)), self._max_bond())
+        self.logger.info('Searching ... ')
+        for ny in range(self.Ny):
+            keep_time = time.time()
+            self.logger.info('Row %d / %d', ny + 1, self.Ny)
+            br = ws['cur']
+            RRat = self._setup_RR(br, ny)
+            br.RL[:br.n] = 1.0
+            for nx in range(self.Nx):
+                self._site_marginals(ws, ws['cur'], RRat, ny, nx)
+                self._site_step(ws, RRat, ny, nx, M, relative_P_cutoff, min_dEng)
+            br = ws['cur']
+            check(lib.tn_row_shift(c.handle, c.stream, br.n, br.vind.stride(0), ptr(br.vind)))
+            self.logger.info('Elapsed: %.2f seconds', time.time() - keep_time)
+        self._finish_search(ws, t_rho, t0)
+        self.logger.info('Elapsed search total: %.2f seconds', self.stats['seconds_rhoT'] + self.stats['seconds_search'])
+        return self.energy
+
+    def gibbs_sampling(self, M=2 ** 10, graduate_truncation=True, Dmax=32, tolS=1e-15, tolV=1e-10, max_sweeps=20):
+        """Sample M configurations from the Boltzmann distribution (tnac4o.py:553-650).  One np.random.rand(M)
+        draw per site, in the reference's order, feeds the inverse-CDF kernel."""
+        dev = self._dev()
+        c = Context.get(dev)
+        t0 = time.time()
+        self.stats = {}
+        self.logger.info('Preprocesing ... ')
+        self._setup_rhoT(graduate_truncation=graduate_truncation, Dmax=Dmax, tolS=tolS, tolV=tolV, max_sweeps=max_sweeps)
+        torch.cuda.synchronize(dev)
+        t_rho = time.time() - t0
+        t0 = time.time()
+        nsites = self.Nx * self.Ny
+        Dcap = self._max_bond()
+        cur = self._Branches(M, self.Nx, nsites, Dcap, dev)
+        nxt = self._Branches(M, self.Nx, nsites, Dcap, dev)
+        cur.n = nxt.n = M
+        ws = {'flag': torch.empty(M, dtype=F64, device=dev), 'gmin': torch.ones(1, dtype=F64, device=dev), 'cand': None,
+              'maxbits': None}
+        parent = torch.empty(M, dtype=torch.int32, device=dev)
+        cell = torch.empty(M, dtype=torch.int32, device=dev)
+        Enew = torch.empty(M, dtype=F64, device=dev)
+        self.logger.info('Sampling ... ')
+        for ny in range(self.Ny):
+            RRat = self._setup_RR(cur, ny)
+            cur.RL[:M] = 1.0
+            sites = self._site_tables()[ny]
+            for nx in range(self.Nx):
+                A = self.rhoT[ny + 1].A[nx]
+                Dl, nd, Dr = A.shape
+                P = self._site_marginals(ws, cur, RRat, ny, nx, want_P='only')
+                uni = torch.from_numpy(np.random.rand(M)).to(dev)
+                check(lib.tn_sample(c.handle, c.stream, sites[nx].ref, M, nx, int(nx > 0), int(ny > 0), ptr(P), ptr(uni),
+                                    ptr(cur.vind), cur.vind.stride(0), ptr(cur.Eng), ptr(parent), ptr(cell), ptr(Enew)))
+                check(lib.tn_materialise(c.handle, c.stream, sites[nx].ref, M, nx, ny * self.Nx + nx, nsites,
+                                         cur.vind.stride(0), Dl, Dr, None, None, None, None, ptr(parent), ptr(cell),
+                                         ptr(Enew), ptr(cur.vind), ptr(cur.states), ptr(cur.root), ptr(cur.RL), ptr(A),
+                                         ptr(nxt.vind), ptr(nxt.states), ptr(nxt.root), ptr(nxt.Eng), None, None,
+                                         ptr(nxt.RL)))
+                cur, nxt = nxt, cur
+            check(lib.tn_row_shift(c.handle, c.stream, M, cur.vind.stride(0), ptr(cur.vind)))
+        torch.cuda.synchronize(dev)
+        self.stats['seconds_rhoT'], self.stats['seconds_search'] = t_rho, time.time() - t0
+        self.energy = cur.Eng[:M].cpu().numpy()
+        self.degeneracy = 0
+        self.states = cur.states[:M].cpu().numpy().astype(int)[:, self.order]
+        self.probability = np.zeros(1)
+        self.discarded_probability = 0
+        self.negative_probability = min(float(ws['gmin'].item()), 0)
+        return self.energy
+
+    sample = gibbs_sampling
+
+    # ------------------------------------------------------------------ low-energy spectrum (droplets)
+    def search_low_energy_spectrum(self, excitations_encoding=1, M=2 ** 10, relative_P_cutoff=1e-6, max_dEng=0.,
+                                   lim_hd=0, min_dEng=1e-12, graduate_truncation=True, Dmax=32, tolS=1e-16,
+                                   tolV=1e-10, max_sweeps=20):
+        """Ground state plus the hierarchy of droplets recorded while merging (tnac4o.py:652-915).
+        ``excitations_encoding=1`` (snake-order independence) is implemented; 2 and 3 are listed as next rows
+        in SURVEY.md section 8(f)."""
+        if excitations_encoding != 1:
+            raise NotImplementedError('Available droplets handling strategy on the GPU path is excitations_encoding = 1.')
+        self.excitations_encoding = excitations_encoding
+        dev = self._dev()
+        c = Context.get(dev)
+        t0 = time.time()
+        self.stats = {}
+        self.logger.info('Preprocesing ... ')
+        self._setup_rhoT(graduate_truncation=graduate_truncation, Dmax=Dmax, tolS=tolS, tolV=tolV, max_sweeps=max_sweeps)
+        torch.cuda.synchronize(dev)
+        t_rho = time.time() - t0
+        t0 = time.time()
+        ws = self._alloc_search(M, int(np.max(self.N)), self._max_bond())
+        ws['want_groups'] = True
+        ws['gmin'] = torch.ones(1, dtype=F64, device=dev)
+        self._exc_initialise()
+        nsites = self.Nx * self.Ny
+        self.logger.info('Searching ... ')
+        for ny in range(self.Ny):
+            self.logger.info('Layer %d / %d', ny + 1, self.Ny)
+            RRat = self._setup_RR(ws['cur'], ny)
+            ws['cur'].RL[:ws['cur'].n] = 1.0
+            for nx in range(self.Nx):
+                self._site_marginals(ws, ws['cur'], RRat, ny, nx)
+                old = ws['cur']
+                groups = self._site_step(ws, RRat, ny, nx, M, relative_P_cutoff, min_dEng)
+                self._record_droplets(ws, old, groups, ny * self.Nx + nx, nsites, max_dEng, lim_hd)
+                self._exc_clear_d()
+            br = ws['cur']
+            check(lib.tn_row_shift(c.handle, c.stream, br.n, br.vind.stride(0), ptr(br.vind)))
+        self._finish_search(ws, t_rho, t0)
+        self.el = self.el[0]
+        for key, (dpos, dstate) in self.d.items():
+            dpos = self.order_i[dpos]
+            srt = dpos.argsort()
+            self.d[key] = (dpos[srt], dstate[srt])
+        return self.energy
+
+    def _record_droplets(self, ws, old, groups, last, nsites, max_dEng, lim_hd):
+        """excitation lists of the new branches (tnac4o.py:844-882).  The XOR differences between the winner and the
+        merged-away members are produced by one integer kernel launch per site (tn_xor_diff); dictionary and tree
+        stay host objects in the reference's own format (they are what save() writes)."""
+        dev = self._dev()
+        c = Context.get(dev)
+        K, G = groups['K'], groups['G']
+        order = groups['order']
+        Bn = ws['cur'].n
+        host = lambda t, n: t[:n].cpu().numpy()
+        g_rep, g_start, g_size = host(ws['g_rep'], G), host(ws['g_start'], G), host(ws['g_size'], G)
+        g_E, g_prob = host(ws['g_E'], G), host(ws['g_prob'], G)
+        sel = host(ws['sel'], Bn)
+        Enew, Pnew = host(ws['Enew'], K), host(ws['Pnew'], K)
+        parent, cell = host(ws['parent'], K), host(ws['cell'], K)
+        # pairs (winner, member) that become droplets
+        pw, pm, pg = [], [], []
+        for j, g in enumerate(sel):
+            if g_size[g] > 1:
+                members = order[g_start[g]:g_start[g] + g_size[g]]
+                gap = Enew[members] - g_E[g]
+                for m in members[(gap <= max_dEng) & (members != g_rep[g])]:
+                    pw.append(g_rep[g]); pm.append(m); pg.append(j)
+        diffs = {}
+        if pw:
+            npairs = len(pw)
+            i32 = lambda a: torch.as_tensor(np.asarray(a, dtype=np.int32), device=dev)
+            row_a, row_b = i32(parent[pw]), i32(parent[pm])
+            cell_a, cell_b = i32(cell[pw]), i32(cell[pm])
+            out_pos = torch.empty((npairs, nsites), dtype=torch.int16, device=dev)
+            out_xor = torch.empty((npairs, nsites), dtype=torch.uint8, device=dev)
+            out_len = torch.empty(npairs, dtype=torch.int32, device=dev)
+            check(lib.tn_xor_diff(c.handle, c.stream, npairs, nsites, last, ptr(old.states), ptr(row_a), ptr(cell_a),
+                                  ptr(row_b), ptr(cell_b), ptr(out_pos), ptr(out_xor), ptr(out_len)))
+            out_pos, out_xor, out_len = out_pos.cpu().numpy(), out_xor.cpu().numpy().view(np.int8), out_len.cpu().numpy()
+            for k in range(npairs):
+                diffs.setdefault(pg[k], []).append((pm[k], out_pos[k, :out_len[k]].astype(np.int64), out_xor[k, :out_len[k]].copy()))
+        new_el = []
+        for j, g in enumerate(sel):
+            winner = g_rep[g]
+            bel = self.el[parent[winner]][:]
+            for m, dpos, dstate in diffs.get(j, []):
+                gap = Enew[m] - g_E[g]
+                if (lim_hd <= 1) or (self._exc_hd(dstate) >= lim_hd):
+                    dfirst = dpos[0]
+                    di = self._exc_add_to_d(dpos, dstate)
+                    sel_sub = [self._exc_cut_energy(sne, max_dEng - (sne[0][0] + gap)) for sne in self.el[parent[m]]
+                               if (sne[0][3] >= dfirst) and (sne[0][0] + gap <= max_dEng)]
+                    bel.append(((gap, di, dfirst, last, Pnew[m] - g_prob[g]), tuple(sel_sub)))
+            new_el.append(bel)
+        self.el = new_el
+
+    # ---- droplet dictionary / tree (host objects in the reference's save format; tnac4o.py:2012-2079, 2249-2285)
+    def _exc_initialise(self):
+        self.d, self.invd, self.el, self.free_d = {}, {}, [[]], 0
+
+    @staticmethod
+    def _exc_get_sh(exc):
+        return (exc[0][0], exc[1][0], exc[0][-1], exc[1][-1])
+
+    def _exc_add_to_d(self, dpos, dstate):
+        sh = self._exc_get_sh((dpos, dstate))
+        for k in self.invd.get(sh, []):
+            if np.array_equal(dpos, self.d[k][0]) and np.array_equal(dstate, self.d[k][1]):
+                return k
+        k = self.free_d
+        self.invd.setdefault(sh, []).append(k)
+        self.d[k] = (dpos, dstate)
+        self.free_d += 1
+        return k
+
+    def _exc_cut_energy(self, exc, maxdE):
+        return (exc[0], tuple(self._exc_cut_energy(se, maxdE - se[0][0]) for se in exc[1] if se[0][0] <= maxdE))
+
+    def _exc_hd(self, dstate):
+        return len(dstate)
+
+    def _exc_get_unique_keys(self, excs):
+        out = set()
+        for e in excs:
+            out.add(e[0][1])
+            out |= self._exc_get_unique_keys(e[1])
+        return out
+
+    def _exc_clear_d(self):
+        live = set()
+        for bel in self.el:
+            live |= self._exc_get_unique_keys(bel)
+        self.d = {k: self.d[k] for k in live}
+        self.invd = {}
+        for k in live:
+            self.invd.setdefault(self._exc_get_sh(self.d[k]), []).append(k)
+
+    def _exc_unpack(self, max_dEng=0., max_states=np.inf):
+        """all droplet combinations below max_dEng, snake-order independence (tnac4o.py:2295-2335)"""
+        Eng, flip = [0.0], [[]]
+        nsites = self.Nx_model * self.Ny_model
+        stacks = [[((0, 0, -1, nsites - 1, 1), tuple(self.el))]]
+        for nn in range(nsites - 1, -1, -1):
+            k = 0
+            while k < len(Eng):
+                for ee in stacks[k][-1][1]:
+                    if ee[0][3] == nn and Eng[k] + ee[0][0] <= max_dEng:
+                        Eng.append(Eng[k] + ee[0][0])
+                        flip.append(flip[k] + [ee[0][1]])
+                        stacks.append(stacks[k] + [ee])
+                    elif ee[0][3] > nn:
+                        break
+                k += 1
+            if len(Eng) > max_states:
+                keep = np.array(Eng).argpartition(max_states)[:max_states]
+                Eng = [Eng[i] for i in keep]
+                flip = [flip[i] for i in keep]
+                stacks = [stacks[i] for i in keep]
+            for k in range(len(Eng)):
+                while stacks[k][-1][0][2] >= nn:
+                    stacks[k].pop()
+        return np.array(Eng), flip
+
+    def decode_low_energy_states(self, max_dEng=0., max_states=1024):
+        """Expand the droplet tree into states (tnac4o.py:1360-1389); the XOR of droplet shapes onto the ground
+        state is one integer kernel over all states (tn_apply_droplets)."""
+        dev = self._dev()
+        c = Context.get(dev)
+        Eng, flip = self._exc_unpack(max_dEng=max_dEng, max_states=max_states)
+        order = Eng.argsort()
+        Eng = Eng[order]
+        count = min(max_states, len(Eng))
+        nsites = self.Nx * self.Ny
+        keys = sorted(self.d)
+        slot = {k: i for i, k in enumerate(keys)}
+        drop_ptr = np.zeros(len(keys) + 1, dtype=np.int32)
+        for i, k in enumerate(keys):
+            drop_ptr[i + 1] = drop_ptr[i] + len(self.d[k][0])
+        drop_pos = np.concatenate([self.d[k][0] for k in keys]).astype(np.int16) if keys else np.zeros(0, np.int16)
+        drop_xor = np.concatenate([self.d[k][1] for k in keys]).astype(np.int8).view(np.uint8) if keys else np.zeros(0, np.uint8)
+        flip_ptr = np.zeros(count + 1, dtype=np.int32)
+        flat = []
+        for i in range(count):
+            f = flip[order[i]]
+            flat.extend(slot[k] for k in f)
+            flip_ptr[i + 1] = len(flat)
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        ground = up(np.ascontiguousarray(self.states[0]).view(np.uint8))
+        out = torch.empty((count, nsites), dtype=torch.uint8, device=dev)
+        t = [up(flip_ptr), up(np.asarray(flat, dtype=np.int32)), up(drop_ptr), up(drop_pos), up(drop_xor)]
+        check(lib.tn_apply_droplets(c.handle, c.stream, count, nsites, ptr(ground), ptr(t[0]), ptr(t[1]), ptr(t[2]),
+                                    ptr(t[3]), ptr(t[4]), ptr(out)))
+        self.energy = Eng + self.energy[0]
+        self.states = out.cpu().numpy().view(np.int8)
+        return Eng[0]
+
+    # ------------------------------------------------------------------ results / files
+    def binary_states(self, number=-1):
+        """cell states -> spins: 1 up, 0 down, 2 inactive (tnac4o.py:261-286)"""
+        ns = self.states.shape[0]
+        ns = ns + number + 1 if number < 0 else min(number, ns)
+        out = np.zeros((ns, self.L), dtype=np.int8) + 2
+        k = -1
+        for ny in range(self.Ny_model):
+            for nx in range(self.Nx_model):
+                k += 1
+                spins = self.ind0[ny][nx]
+                out[:, spins] = (1 - cell_bits(len(spins)))[self.states[:ns, k]]
+        return out
+
+    def save(self, file_name):
+        """np.save of the result dictionary in the reference's layout (tnac4o.py:200-233)"""
+        d = {'mode': self.mode, 'rotation': self.rotation, 'energy': self.energy, 'probability': self.probability,
+             'degeneracy': self.degeneracy, 'states': self.states, 'discarded_probability': self.discarded_probability,
+             'negative_probability': self.negative_probability, 'Nx': self.Nx_model, 'Ny': self.Ny_model, 'Nc': self.Nc,
+             'beta': self.beta, 'ind': self.ind0}
+        if hasattr(self, 'excitations_encoding'):
+            d.update({'excitations_encoding': self.excitations_encoding, 'd': self.d, 'invd': self.invd, 'el': self.el,
+                      'free_d': self.free_d})
+        np.save(file_name, d)
+
+    def show_properties(self):
+        print("L:     ", self.L)
+        print("Ny:    ", self.Ny)
+        print("Nx:    ", self.Nx)
+        print("Beta:  ", self.beta)
+
+    def show_solution(self, state=False):
+        if len(self.energy) > 0:
+            print("Energy            : %4.6f" % self.energy[0])
+            print("Degeneracy        : %2d" % self.degeneracy)
+            print("log2(Probability) : %0.2e" % self.probability[0])
+            print("Discarder log2(P) : %0.2e" % self.discarded_probability)
+            print("Min P (err)       : %0.2e" % self.negative_probability)
+            print("# of states       : %1d" % len(self.energy))
+            print("Rotation/direction: %1d" % self.rotation)
+            if state:
+                print(self.states[0])
+        else:
+            print('No solution to show.')
+
+    def exc_print(self):
+        self._exc_print(self.el, 1)
+
+    def _exc_print(self, el, layer):
+        for exc in el:
+            kk = self.d[exc[0][1]]
+            print((3 * layer - 3) * ' ' + "|- %0.4f " % (exc[0][0]) + ' : ' + ' '.join(map(str, kk[0])) + ' | ' +
+                  ' '.join(map(str, kk[1])))
+            self._exc_print(exc[1], layer + 1)

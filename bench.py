@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""Headline benchmark: L=2048 chimera ground-state search, seconds per instance (+ branch-marginals/s).
+
+    python bench.py --gpus N --steps K --warmup W            # the sm_100a path (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference algorithm (numpy port) on the host cores
+
+A step is one pass of the hot path over one instance: boundary-MPS build (_setup_rhoT) + branch-and-bound
+(search_ground_state) at M = 2^10, Dmax = 32, beta = 3, relative_P_cutoff = 1e-8, no preconditioning
+(BASELINE.json config 4, the M = 2^10 variant the north star quotes its target on).  Rank 0 solves droplet
+instance 001 (checked against the reference's golden energy); other ranks solve synthetic instances with the
+same coupling pattern (weak scaling: independent instances, no data-path collective -- DESIGN.md section (e)).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+CFG = dict(L=2048, Nx=16, Ny=16, Nc=8, beta=3.0, M=2 ** 10, Dmax=32, relative_P_cutoff=1e-8)
+METRIC = 'L=2048 chimera ground-state search, seconds per instance'
+UNIT = 's/instance'
+
+
+def instance_couplings(rank):
+    """rank 0: droplet instance 001 as e01 prepares it; rank r > 0: same coupling pattern, values redrawn from the
+    file's value set with seed r (synthetic family A)"""
+    from conftest import droplet_couplings
+    J = droplet_couplings(CFG['L'], 1)
+    if rank == 0:
+        return J
+    rng = np.random.default_rng(rank)
+    vals = np.array([v for _, _, v in J])
+    return [[i, j, float(v)] for (i, j, _), v in zip(J, rng.permutation(vals))]
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
+                                          '--format=csv,noheader,nounits', '-lms', '200'], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.lines:
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(smax) if smax else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def fp64_peak(torch, dev):
+    """FP64 roofline denominator: MEASURED_PEAKS.json has no FP64 entry, so it is measured here the way the file's
+    bf16 number was: cuBLAS DGEMM 8192^3 through torch.matmul, best of 5, CUDA events."""
+    n = 8192
+    a = torch.randn((n, n), dtype=torch.float64, device=dev)
+    b = torch.randn((n, n), dtype=torch.float64, device=dev)
+    torch.matmul(a, b)
+    best = float('inf')
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b); e1.record(); e1.synchronize()
+        best = min(best, e0.elapsed_time(e1) * 1e-3)
+    del a, b
+    torch.cuda.empty_cache()
+    return 2.0 * n ** 3 / best / 1e12
+
+
+def instrument_gemm(ops, torch):
+    """wrap ops.gemm with CUDA events on the launching stream (roofline pass only)"""
+    log = []
+    raw = ops.gemm
+
+    def timed(A, B, transA=False, transB=False, out=None, alpha=1.0, beta=0.0):
+        M = A.shape[1] if transA else A.shape[0]
+        K = A.shape[0] if transA else A.shape[1]
+        N = B.shape[0] if transB else B.shape[1]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = raw(A, B, transA, transB, out, alpha, beta)
+        e1.record()
+        log.append((2.0 * M * N * K, e0, e1))
+        return r
+    ops.gemm = timed
+    return log, raw
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device -- the sm_100a path has no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    import tnac4o_b200
+    from tnac4o_b200 import ops, mps
+
+    J = instance_couplings(rank)
+    t_prep = time.time()
+    ins = tnac4o_b200.tnac4o(mode='Ising', Nx=CFG['Nx'], Ny=CFG['Ny'], Nc=CFG['Nc'], J=J, beta=CFG['beta'], device=dev)
+    t_prep = time.time() - t_prep
+    ins._site_tables()                                    # inputs resident in HBM before the timed region
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def step(e2e):
+        if e2e:
+            ins._sites = None                             # host tables -> HBM inside the timed region
+        flush.fill_(1)
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ins.search_ground_state(M=CFG['M'], relative_P_cutoff=CFG['relative_P_cutoff'], Dmax=CFG['Dmax'])
+        e1.record(); e1.synchronize()
+        return e0.elapsed_time(e1) * 1e-3, time.perf_counter() - t0, dict(ins.stats)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step(False)
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    launches0 = ops.launch_count(dev)
+    t_begin = time.perf_counter()
+    dev_s, stats = [], []
+    for _ in range(args.steps):
+        d, _, st = step(False)
+        dev_s.append(d); stats.append(st)
+    barrier()
+    total = time.perf_counter() - t_begin
+    launches = ops.launch_count(dev) - launches0
+    clk = clocks.stop()
+    # end-to-end through the public API: host tables uploaded and results read back inside the timed region
+    barrier()
+    t_begin = time.perf_counter()
+    for _ in range(args.steps):
+        step(True)
+    barrier()
+    total_e2e = time.perf_counter() - t_begin
+    h2d = sum(t.numel() * t.element_size() for row in ins._sites for s in row
+              for t in (s.Wlu, s.WtrU, s.Wmpo, s.dmap, s.rmap, s.Es, s.Esl, s.Esu))
+    d2h = ins.energy.nbytes + ins.states.nbytes + ins.probability.nbytes + 3 * 8
+
+    if world > 1:
+        t = torch.tensor([total, total_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total, total_e2e = t.tolist()
+        cnt = torch.tensor([launches, sum(s['marginals'] for s in stats), sum(s['seconds_search'] for s in stats)],
+                           dtype=torch.float64, device=dev)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        launches_all, marg_all, search_s_all = cnt.tolist()
+    else:
+        launches_all, marg_all = launches, sum(s['marginals'] for s in stats)
+        search_s_all = sum(s['seconds_search'] for s in stats)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    instances = args.steps * world
+    value = total / instances
+    # ---- parity guard on the timed workload: golden energy of instance 001 (groundstates_otn2d.txt:1)
+    from conftest import droplet_golden
+    e_file, _ = droplet_golden(CFG['L'], 1)
+    parity_ok = bool(abs(ins.energy[0] - e_file) < 1e-5)
+
+    # ---- roofline pass (one extra, instrumented step; not part of the timed region)
+    peak = fp64_peak(torch, dev)
+    log, raw = instrument_gemm(ops, torch)
+    step(False)
+    torch.cuda.synchronize(dev)
+    ops.gemm = raw
+    flops = sum(f for f, _, _ in log)
+    secs = sum(a.elapsed_time(b) for _, a, b in log) * 1e-3
+    big = [(f, a.elapsed_time(b) * 1e-3) for f, a, b in log if f >= 1e9]
+    roofline = {'bound': 'tensor', 'kernel': 'gemm_kernel (DMMA m8n8k4 f64)', 'achieved': flops / secs / 1e12 if secs else None,
+                'peak': peak, 'unit': 'TFLOP/s', 'frac': (flops / secs / 1e12 / peak) if secs else None, 'traffic': None,
+                'launches': len(log), 'gemm_seconds_per_step': secs,
+                'achieved_large_gemms': (sum(f for f, _ in big) / sum(t for _, t in big) / 1e12) if big else None,
+                'peak_source': 'measured here: torch.matmul f64 8192^3 (cuBLAS DGEMM), best of 5 -- MEASURED_PEAKS.json has no FP64 entry',
+                'measured_in': 'one extra instrumented step after the timed region (CUDA events around every GEMM launch)'}
+    # ---- CPU baseline: the numpy port of the reference on a bounded sample
+    cpu = cpu_sample(J)
+    out = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+           'ms_per_step': 1e3 * total / args.steps, 'higher_is_better': False, 'scaling': 'weak', 'vs_baseline': None,
+           'dtype': 'f64', 'data': 'droplet instance 001 (rank 0) + synthetic couplings on the same chimera pattern (other ranks)',
+           'config': {'workload': 'e01 ground-state search L=2048 (16x16x8 chimera), M=2^10, Dmax=32, beta=3, P_cutoff=1e-8, no preconditioning',
+                      'l2': 'flushed between steps (256 MiB write)', 'parity_energy_matches_golden': parity_ok},
+           'seconds_rhoT': float(np.mean([s['seconds_rhoT'] for s in stats])),
+           'seconds_search': float(np.mean([s['seconds_search'] for s in stats])),
+           'branch_marginals_per_s': marg_all / search_s_all * world if search_s_all else None,
+           'device_seconds_per_step_rank0': float(np.mean(dev_s)),
+           'host_model_prep_seconds': t_prep,
+           'e2e': {'value': total_e2e / instances, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
+           'gpu_launches': int(launches_all), 'clocks': clk, 'roofline': roofline, 'cpu_baseline': cpu}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def _sample_once(J):
+    """Bounded sample of the workload for the numpy port: a 4-row slab of the instance (same Nx, M, Dmax), which
+    contains every kind of row of the 16-row lattice.  Returns timings that extrapolate to the whole instance."""
+    import warnings
+    warnings.filterwarnings('ignore')
+    from oracle import RefSolver
+    rows = 4
+    Nx, Nc = CFG['Nx'], CFG['Nc']
+    keep = rows * Nx * Nc
+    Jsub = [[i, j, v] for i, j, v in J if i < keep and j < keep]
+    ins = RefSolver(mode='Ising', Nx=Nx, Ny=rows, Nc=Nc, J=Jsub, beta=CFG['beta'])
+    t_rows = []
+    from oracle.mps_ref import RefMPS
+    ins.rhoT = [None] * (rows + 1)
+    ins.rhoT_overlap, ins.rhoT_discarded = [1] * (rows + 1), [0] * (rows + 1)
+    ins.rhoT[-1] = RefMPS(Nx, d=1)
+    for ny in range(rows - 1, -1, -1):
+        t0 = time.perf_counter()
+        W = [ins.traced_mpo(ny, nx) for nx in range(Nx)]
+        psi = ins.rhoT[ny + 1].copy()
+        psi.apply_mpo(W, conj=True)
+        psi.compress(CFG['Dmax'], 1e-16, 1e-10, 20, True)
+        ins.rhoT[ny] = psi
+        t_rows.append(time.perf_counter() - t0)
+    # search: first lattice row only (branch count saturates at M within the first sites)
+    ins._setup_rhoT = lambda *a, **k: None
+    t0 = time.perf_counter()
+    count = search_rows(ins, 1)
+    t_search = time.perf_counter() - t0
+    return {'t_rows': t_rows, 't_search_row': t_search, 'marginals_row': count}
+
+
+def search_rows(ins, nrows):
+    """the oracle's branch-and-bound restricted to the first nrows lattice rows (timing sample)"""
+    full, order = ins.Ny, ins.order
+    ins.Ny, ins.order = nrows, np.arange(nrows * ins.Nx)
+    try:
+        ins.search_ground_state(M=CFG['M'], relative_P_cutoff=CFG['relative_P_cutoff'], Dmax=CFG['Dmax'])
+    finally:
+        ins.Ny, ins.order = full, order
+    return ins.marginals_evaluated
+
+
+def extrapolate(s):
+    Ny = CFG['Ny']
+    bottom, second, steady, top = s['t_rows']          # lattice rows Ny-1 (bond 16), Ny-2 (256), interior (512), 0 (no up leg)
+    rho = bottom + second + steady * (Ny - 3) + top
+    search = s['t_search_row'] * Ny
+    return rho + search, rho, search
+
+
+def cpu_sample(J):
+    os.environ.setdefault('OPENBLAS_NUM_THREADS', '1')
+    s = _sample_once(J)
+    total, rho, search = extrapolate(s)
+    return {'value': total, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+            'seconds_rhoT_est': rho, 'seconds_search_est': search,
+            'branch_marginals_per_s': s['marginals_row'] / s['t_search_row'],
+            'sample': 'numpy port of the reference (oracle/), 1 BLAS thread: boundary-MPS build of a 4-row slab of the 16 lattice rows '
+                      '(bond 16 -> 256 -> 512; the interior row is the steady-state cost, x13) + branch-and-bound over the first '
+                      'lattice row (x16); same instance, Nx, M, Dmax'}
+
+
+def _worker(rank, q):
+    os.environ['OPENBLAS_NUM_THREADS'] = '1'
+    os.environ['OMP_NUM_THREADS'] = '1'
+    q.put(_sample_once(instance_couplings(rank)))
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    import psutil
+    cores = len(os.sched_getaffinity(0))
+    mem_gb = psutil.virtual_memory().available / 2 ** 30
+    workers = int(max(1, min(cores, mem_gb // 6, 64)))
+    ctx = mp.get_context('spawn')
+
+    def step():
+        q = ctx.Queue()
+        procs = [ctx.Process(target=_worker, args=(r, q)) for r in range(workers)]
+        t0 = time.perf_counter()
+        for p in procs:
+            p.start()
+        res = [q.get() for _ in procs]
+        for p in procs:
+            p.join()
+        return time.perf_counter() - t0, res
+
+    for _ in range(args.warmup):
+        step()
+    times, results = [], []
+    for _ in range(args.steps):
+        t, r = step()
+        times.append(t); results.extend(r)
+    # every worker processed one bounded sample; scale each worker's timings to a whole instance
+    per_instance = float(np.mean([extrapolate(r)[0] for r in results]))
+    value = per_instance / workers               # instances run concurrently, one per core
+    marg = float(np.mean([r['marginals_row'] / r['t_search_row'] for r in results])) * workers
+    cpu = {'value': value, 'unit': UNIT, 'cores': workers, 'kind': 'port',
+           'sample': 'numpy port of the reference (oracle/): %d concurrent single-thread workers (1 BLAS thread each is the '
+                     'fastest setting, SURVEY.md section 6), each timing a 4-row slab of the 16 lattice rows of the boundary-MPS build '
+                     '(steady-state interior row x13) and the first lattice row of the search (x16); value = extrapolated seconds per '
+                     'instance / workers' % workers}
+    out = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+           'warmup': args.warmup, 'ms_per_step': 1e3 * float(np.mean(times)), 'higher_is_better': False, 'scaling': 'weak',
+           'vs_baseline': None, 'dtype': 'f64', 'data': 'droplet instance 001 + synthetic couplings on the same chimera pattern',
+           'config': {'workload': 'e01 ground-state search L=2048 (16x16x8 chimera), M=2^10, Dmax=32, beta=3, P_cutoff=1e-8, no preconditioning'},
+           'single_thread_seconds_per_instance': per_instance, 'branch_marginals_per_s': marg,
+           'cpu_baseline': cpu, 'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+           'gpu_launches': 0}
+    print(json.dumps(out))
+
+
+if __name__ == '__main__':
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    a = ap.parse_args()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_gpu(a)

@@ -1,14 +1,20 @@
 // Thin SVD by one-sided (Hestenes) Jacobi with block round-robin ordering -- replaces mps.svd / mps.svd_S
 // (mps.py:24-40, 62-73: LAPACK gesdd with gesvd fall-back).
 //
-// The matrix is held as "extended columns" E[k] = [ w_k (length a) | j_k (length ext) ]: w_k are the columns
-// being orthogonalised, j_k the accumulated rotations (identity at start, ext = 0 when only singular values
-// are wanted).  A CTA owns a pair of column blocks in shared memory, runs cyclic Jacobi among them with one
-// warp per column pair (dot products reduced with warp shuffles) and writes them back; block pairs follow a
-// round-robin tournament so that all pairs meet once per sweep.  Small problems are resident in one CTA and
-// iterate to convergence inside a single launch.  Rotations are computed from the 2x2 Gram of the two
-// columns, which keeps small singular values accurate to high relative precision; a Gram/eigh formulation of
-// the whole matrix is deliberately NOT used (hard part 1-iii).
+// The matrix is held as "extended vectors" E[k] = [ w_k (length a) | j_k (length ext) ]: w_k are the rows or
+// columns of C being orthogonalised, j_k the accumulated rotations (identity at start, ext = 0 when only
+// singular values are wanted).  A CTA owns a pair of vector blocks in shared memory, runs cyclic Jacobi among
+// them with one warp per pair (dot products reduced with warp shuffles) and writes them back; block pairs
+// follow a round-robin tournament so that all pairs meet once per sweep.  Small problems are resident in one
+// CTA and iterate to convergence inside a single launch.  Rotations are computed from the 2x2 Gram of the two
+// vectors only, which keeps small singular values accurate to high relative precision; a Gram/eigh formulation
+// of the whole matrix is deliberately NOT used (hard part 1-iii).
+//
+// Deflation.  The centre matrices of the boundary MPS are triangular QR factors whose singular values span
+// 1 ... 1e-40 (measured on the reference at L = 2048).  Everything below eps * S0 is discarded by the caller
+// (mps.py:805-806), so vectors whose norm is below DEAD_FLOOR * ||C||_F (1e-3 * eps) are never rotated: they are
+// reported as exact zero singular values.  The orientation (rows or columns of C) with fewer live vectors is
+// orthogonalised -- for a triangular factor that is the graded side, typically 100-200 of 512.
 #include "common.cuh"
 
 namespace {
@@ -16,15 +22,77 @@ namespace {
 constexpr int JT = 512;              // threads per CTA
 constexpr int JW = JT / 32;
 constexpr size_t SMEM_LIMIT = 200 * 1024;
+constexpr double DEAD_FLOOR = 2.2e-19;
+constexpr int MAX_SWEEPS = 60;
 
-// E <- columns (or rows) of C, plus identity in the extension
-__global__ void jacobi_init_kernel(const double* __restrict__ C, int ldc, int m, int n, int transposed, double* E,
-                                   int ldw, int a, int ext, int nc) {
+struct SvdMeta {
+    int use_rows;      // 1: the rows of C are orthogonalised, 0: the columns
+    int nlive;
+    double fro2;
+};
+
+// squared norms of all rows (blocks 0..m-1) and columns (blocks m..m+n-1)
+__global__ void svd_norms_kernel(const double* __restrict__ C, int ldc, int m, int n, double* __restrict__ norms2) {
+    __shared__ double red[8];
+    int b = blockIdx.x;
+    double s = 0.0;
+    if (b < m) {
+        for (int j = threadIdx.x; j < n; j += blockDim.x) { double v = C[(int64_t)b * ldc + j]; s += v * v; }
+    } else {
+        int j = b - m;
+        for (int i = threadIdx.x; i < m; i += blockDim.x) { double v = C[(int64_t)i * ldc + j]; s += v * v; }
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        norms2[b] = t;
+    }
+}
+
+// single thread block: Frobenius norm, live flags, orientation, compact index list
+__global__ void svd_select_kernel(const double* __restrict__ norms2, int m, int n, int force_rows, int deflate,
+                                  SvdMeta* meta, int* __restrict__ live_idx) {
+    __shared__ double fro2_s;
+    __shared__ int cnt_s[2];
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < m; ++i) t += norms2[i];
+        fro2_s = t;
+        cnt_s[0] = cnt_s[1] = 0;
+    }
+    __syncthreads();
+    const double floor_cnt = DEAD_FLOOR * DEAD_FLOOR * fro2_s;      // orientation: the side with fewer live vectors
+    const double floor2 = deflate ? floor_cnt : -1.0;               // liveness: everything when not deflating
+    int cr = 0, cc = 0;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) cr += (norms2[i] > floor_cnt);
+    for (int j = threadIdx.x; j < n; j += blockDim.x) cc += (norms2[m + j] > floor_cnt);
+    atomicAdd(&cnt_s[0], cr);
+    atomicAdd(&cnt_s[1], cc);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int use_rows = (force_rows >= 0) ? force_rows : (cnt_s[0] <= cnt_s[1]);
+        int cnt = 0;
+        if (use_rows) { for (int i = 0; i < m; ++i) if (norms2[i] > floor2) live_idx[cnt++] = i; }
+        else { for (int j = 0; j < n; ++j) if (norms2[m + j] > floor2) live_idx[cnt++] = j; }
+        meta->use_rows = use_rows;
+        meta->nlive = cnt;
+        meta->fro2 = fro2_s;
+    }
+}
+
+// E[e] = [ live vector e of C | unit vector e ]
+__global__ void jacobi_init_kernel(const double* __restrict__ C, int ldc, const SvdMeta* __restrict__ meta,
+                                   const int* __restrict__ live_idx, double* __restrict__ E, int ldw, int a, int ext, int nc) {
+    const int use_rows = meta->use_rows;
     int64_t total = (int64_t)nc * ldw;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int k = (int)(i / ldw), e = (int)(i % ldw);
+        int src = live_idx[k];
         double v;
-        if (e < a) v = transposed ? C[(int64_t)k * ldc + e] : C[(int64_t)e * ldc + k];
+        if (e < a) v = use_rows ? C[(int64_t)src * ldc + e] : C[(int64_t)e * ldc + src];
         else v = (e - a == k) ? 1.0 : 0.0;
         E[i] = v;
     }
@@ -33,8 +101,8 @@ __global__ void jacobi_init_kernel(const double* __restrict__ C, int ldc, int m,
 // one tournament round over block pairs; CTA b handles the pair given by the circle method
 __global__ void __launch_bounds__(JT, 1)
 jacobi_round_kernel(double* __restrict__ E, int ldw, int a, int nc, int bsz, int nblocks, int round, int inner_max,
-                    double tol, unsigned int* rot_count) {
-    extern __shared__ __align__(16) double S[];      // [cols_here][ldw]
+                    double tol, const SvdMeta* __restrict__ meta, unsigned int* rot_count) {
+    extern __shared__ __align__(16) double S[];      // [vectors here][ldw]
     __shared__ int col_of[512];
     __shared__ unsigned int sweep_rot;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -47,6 +115,7 @@ jacobi_round_kernel(double* __restrict__ E, int ldw, int a, int nc, int bsz, int
         b1 = (i == 0) ? n1 : (round + n1 - i) % n1;
     }
     if (b0 >= nblocks || b1 >= nblocks) return;      // partner is the phantom block of an odd tournament
+    const double floor2 = DEAD_FLOOR * DEAD_FLOOR * meta->fro2;
     int c0 = b0 * bsz, n0 = min(bsz, nc - c0);
     int c1 = b1 * bsz, n1c = min(bsz, nc - c1);
     const int ncol = n0 + n1c;
@@ -66,9 +135,8 @@ jacobi_round_kernel(double* __restrict__ E, int ldw, int a, int nc, int bsz, int
         unsigned int my_rot = 0;
         for (int r = 0; r < (nce > 1 ? r1 : 0); ++r) {
             for (int i = warp; i < half; i += JW) {
-                int p = (nce == 2) ? 0 : (r + i) % r1;
+                int p = (r + i) % r1;
                 int q = (i == 0) ? r1 : (r + r1 - i) % r1;
-                if (nce == 2) q = 1;
                 if (p >= ncol || q >= ncol) continue;
                 if (p > q) { int t = p; p = q; q = t; }
                 double* xp = S + (int64_t)p * ldw;
@@ -79,7 +147,7 @@ jacobi_round_kernel(double* __restrict__ E, int ldw, int a, int nc, int bsz, int
                     app += u * u; aqq += v * v; apq += u * v;
                 }
                 app = warp_sum(app); aqq = warp_sum(aqq); apq = warp_sum(apq);
-                if (fabs(apq) > tol * sqrt(app) * sqrt(aqq) && app > 0.0 && aqq > 0.0) {
+                if (fabs(apq) > tol * sqrt(app) * sqrt(aqq) && app > floor2 && aqq > floor2) {
                     double zeta = (aqq - app) / (2.0 * apq);
                     double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
                     double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
@@ -107,19 +175,22 @@ jacobi_round_kernel(double* __restrict__ E, int ldw, int a, int nc, int bsz, int
     if (lane == 0 && my_rot_total) atomicAdd(rot_count, my_rot_total);
 }
 
-// norms -> S (sorted descending), singular vectors with the sign rule of mps.svd (mps.py:35-39)
+// norms -> S (sorted descending, dead vectors = exact zeros at the end), singular vectors with the sign rule of
+// mps.svd (mps.py:35-39).  U and Vt must be zero-filled by the caller.
 __global__ void __launch_bounds__(JT, 1)
-jacobi_finish_kernel(const double* __restrict__ E, int ldw, int a, int ext, int nc, int transposed, double* __restrict__ U,
-                     int ldu, double* __restrict__ Sout, double* __restrict__ Vt, int ldvt, double* sv_tmp, int* rank_tmp) {
+jacobi_finish_kernel(const double* __restrict__ E, int ldw, int a, int ext, int nc, int kfull, int has_dead,
+                     const SvdMeta* __restrict__ meta, const int* __restrict__ live_idx, double* __restrict__ U, int ldu,
+                     double* __restrict__ Sout, double* __restrict__ Vt, int ldvt, double* sv_tmp, int* rank_tmp) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int use_rows = meta->use_rows;
     for (int k = warp; k < nc; k += JW) {
         const double* w = E + (int64_t)k * ldw;
-        // scaled 2-norm is unnecessary: entries are normalised to O(1) by nfactor before every SVD
         double s = 0.0;
-        for (int e = lane; e < a; e += 32) s += w[e] * w[e];
+        for (int e = lane; e < a; e += 32) s += w[e] * w[e];     // entries are O(1) after nfactor: no scaling needed
         s = warp_sum(s);
         if (lane == 0) sv_tmp[k] = sqrt(s);
     }
+    for (int k = nc + tid; k < kfull; k += JT) Sout[k] = 0.0;
     __syncthreads();
     for (int k = tid; k < nc; k += JT) {
         double sk = sv_tmp[k];
@@ -139,17 +210,19 @@ jacobi_finish_kernel(const double* __restrict__ E, int ldw, int a, int ext, int 
         const double sk = sv_tmp[k];
         const double inv = (sk > 0.0) ? 1.0 / sk : 0.0;
         const int r = rank_tmp[k];
-        double mxw = -INFINITY, mnw = INFINITY, mxj = -INFINITY, mnj = INFINITY;
+        // sign rule: flip when |min| > max holds for both the left and the right vector (zeros of dead entries count)
+        double mxw = -INFINITY, mnw = INFINITY, mxj = has_dead ? 0.0 : -INFINITY, mnj = -mxj;
         for (int e = lane; e < a; e += 32) { double v = w[e] * inv; mxw = fmax(mxw, v); mnw = fmin(mnw, v); }
         for (int e = lane; e < ext; e += 32) { double v = jv[e]; mxj = fmax(mxj, v); mnj = fmin(mnj, v); }
         mxw = warp_max(mxw); mnw = warp_min(mnw); mxj = warp_max(mxj); mnj = warp_min(mnj);
         const double sg = ((fabs(mnw) > mxw) && (fabs(mnj) > mxj)) ? -1.0 : 1.0;
-        if (!transposed) {
-            for (int e = lane; e < a; e += 32) U[(int64_t)e * ldu + r] = sg * w[e] * inv;      // a = m
-            for (int e = lane; e < ext; e += 32) Vt[(int64_t)r * ldvt + e] = sg * jv[e];        // ext = n
+        if (use_rows) {
+            // C = J S W^T: U[:, r] = j-part scattered through the live row list, Vt[r, :] = w / s
+            for (int e = lane; e < ext; e += 32) U[(int64_t)live_idx[e] * ldu + r] = sg * jv[e];
+            for (int e = lane; e < a; e += 32) Vt[(int64_t)r * ldvt + e] = sg * w[e] * inv;
         } else {
-            for (int e = lane; e < ext; e += 32) U[(int64_t)e * ldu + r] = sg * jv[e];          // ext = m
-            for (int e = lane; e < a; e += 32) Vt[(int64_t)r * ldvt + e] = sg * w[e] * inv;     // a = n
+            for (int e = lane; e < a; e += 32) U[(int64_t)e * ldu + r] = sg * w[e] * inv;
+            for (int e = lane; e < ext; e += 32) Vt[(int64_t)r * ldvt + live_idx[e]] = sg * jv[e];
         }
     }
 }
@@ -175,55 +248,92 @@ extern "C" int tn_svd(tn_ctx* ctx, void* stream, int m, int n, const double* C, 
                       double* Vt, int ldvt, int want_vectors, int* h_sweeps) {
     TN_REQUIRE(ctx != nullptr, "null context");
     TN_REQUIRE(m >= 1 && n >= 1, "empty matrix");
+    TN_REQUIRE(m <= 4096 && n <= 4096, "matrix too large for the Jacobi SVD");
     cudaStream_t st = as_stream(stream);
-    const int transposed = (m < n);
-    const int a = transposed ? n : m;
-    const int nc = transposed ? m : n;
+    const int kfull = m < n ? m : n;
+
+    // ---- norms, orientation, live vectors
+    size_t head_bytes = ((size_t)(m + n) * sizeof(double) + (size_t)(m + n) * sizeof(int) + sizeof(SvdMeta) + 64 + 15) & ~(size_t)15;
+    char* head = (char*)tn_scratch(ctx, TN_SLOT_MISC, head_bytes + 256);
+    if (!head) return TN_ERR_NOMEM;
+    double* norms2 = (double*)head;
+    int* live_idx = (int*)(norms2 + (m + n));
+    SvdMeta* meta = (SvdMeta*)(((uintptr_t)(live_idx + (m + n)) + 15) & ~(uintptr_t)15);
+    unsigned int* rot = (unsigned int*)(meta + 1);
+    svd_norms_kernel<<<m + n, 128, 0, st>>>(C, ldc, m, n, norms2);
+    TN_LAUNCHED(ctx);
+    // a wide or tall matrix is always handled on its short side (k vectors of the long length); for a square one
+    // the side with fewer live vectors is chosen on the device
+    const int force = (m < n) ? 1 : (m > n ? 0 : -1);
+    const int a = (m < n) ? n : m;
+    // small problems: everything resident in one CTA, no deflation, no host read-back
+    const int ldw_full = a + (want_vectors ? kfull : 0);
+    const bool small = (size_t)kfull * ldw_full * sizeof(double) <= SMEM_LIMIT && kfull <= 512;
+    svd_select_kernel<<<1, 256, 0, st>>>(norms2, m, n, force, small ? 0 : 1, meta, live_idx);
+    TN_LAUNCHED(ctx);
+    int nc = kfull;
+    if (!small) {
+        // the launch geometry depends on the number of live vectors: one host read-back
+        SvdMeta* hmeta = (SvdMeta*)((char*)ctx->pinned + 256);
+        TN_CUDA(cudaMemcpyAsync(hmeta, meta, sizeof(SvdMeta), cudaMemcpyDeviceToHost, st));
+        TN_CUDA(cudaStreamSynchronize(st));
+        nc = hmeta->nlive;
+    }
     const int ext = want_vectors ? nc : 0;
     const int ldw = a + ext;
-    TN_REQUIRE(nc <= 4096, "matrix too large for the Jacobi SVD");
-    TN_REQUIRE((size_t)2 * ldw * sizeof(double) <= SMEM_LIMIT, "column too long for the shared-memory Jacobi kernel");
+    const int has_dead = nc < kfull;
 
+    if (want_vectors) {
+        TN_CUDA(cudaMemset2DAsync(U, (size_t)ldu * sizeof(double), 0, (size_t)kfull * sizeof(double), m, st));
+        TN_CUDA(cudaMemset2DAsync(Vt, (size_t)ldvt * sizeof(double), 0, (size_t)n * sizeof(double), kfull, st));
+    }
+    int sweeps = 0;
+    if (nc == 0) {
+        TN_CUDA(cudaMemsetAsync(S, 0, (size_t)kfull * sizeof(double), st));
+        if (h_sweeps) *h_sweeps = 0;
+        return TN_OK;
+    }
+    TN_REQUIRE((size_t)2 * ldw * sizeof(double) <= SMEM_LIMIT, "vectors too long for the shared-memory Jacobi kernel");
     size_t bytes = (size_t)nc * ldw * sizeof(double) + (size_t)nc * (sizeof(double) + sizeof(int)) + 64;
     char* ws = (char*)tn_scratch(ctx, TN_SLOT_SVD, bytes);
     if (!ws) return TN_ERR_NOMEM;
     double* E = (double*)ws;
     double* sv_tmp = E + (size_t)nc * ldw;
     int* rank_tmp = (int*)(sv_tmp + nc);
-    unsigned int* rot = (unsigned int*)(rank_tmp + nc + (nc & 1));
-
     {
         int64_t total = (int64_t)nc * ldw;
         int blocks = (int)((total + 255) / 256 < 8 * ctx->sm_count ? (total + 255) / 256 : 8 * ctx->sm_count);
-        jacobi_init_kernel<<<blocks, 256, 0, st>>>(C, ldc, m, n, transposed, E, ldw, a, ext, nc);
+        jacobi_init_kernel<<<blocks, 256, 0, st>>>(C, ldc, meta, live_idx, E, ldw, a, ext, nc);
         TN_LAUNCHED(ctx);
     }
     int cmax = (int)(SMEM_LIMIT / ((size_t)ldw * sizeof(double)));
     cmax -= (cmax & 1);
     if (cmax > 512) cmax = 512;
     const double tol = sqrt((double)a) * 2.220446049250313e-16;
-    int sweeps = 0;
     unsigned int* h_rot = (unsigned int*)ctx->pinned;
     TN_CUDA(cudaFuncSetAttribute(jacobi_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
     if (nc <= cmax) {
         // resident: one CTA iterates to convergence
-        int bsz = (nc + 1) / 2, nblocks = (nc > bsz) ? 2 : 1;
-        size_t smem = (size_t)nc * ldw * sizeof(double);
-        TN_CUDA(cudaMemsetAsync(rot, 0, sizeof(unsigned int), st));
         if (nc > 1) {
-            jacobi_round_kernel<<<1, JT, smem, st>>>(E, ldw, a, nc, bsz, nblocks, 0, 60, tol, rot);
+            int bsz = (nc + 1) / 2;
+            size_t smem = (size_t)nc * ldw * sizeof(double);
+            TN_CUDA(cudaMemsetAsync(rot, 0, sizeof(unsigned int), st));
+            jacobi_round_kernel<<<1, JT, smem, st>>>(E, ldw, a, nc, bsz, 2, 0, MAX_SWEEPS, tol, meta, rot);
             TN_LAUNCHED(ctx);
         }
         sweeps = 1;
     } else {
-        int bsz = cmax / 2, nblocks = ceil_div(nc, bsz);
+        // smaller blocks than shared memory would allow keep more SMs busy and the inner sweeps short
+        int bsz = cmax / 2;
+        while (bsz > 8 && ceil_div(nc, bsz) < 16) bsz = (bsz + 1) / 2;
+        int nblocks = ceil_div(nc, bsz);
         int npe = nblocks + (nblocks & 1);
         size_t smem = (size_t)2 * bsz * ldw * sizeof(double);
         bool converged = false;
-        for (sweeps = 0; sweeps < 60 && !converged;) {
+        for (sweeps = 0; sweeps < MAX_SWEEPS && !converged;) {
             TN_CUDA(cudaMemsetAsync(rot, 0, sizeof(unsigned int), st));
             for (int r = 0; r < npe - 1; ++r) {
-                jacobi_round_kernel<<<npe / 2, JT, smem, st>>>(E, ldw, a, nc, bsz, nblocks, r, 2, tol, rot);
+                jacobi_round_kernel<<<npe / 2, JT, smem, st>>>(E, ldw, a, nc, bsz, nblocks, r, 2, tol, meta, rot);
                 TN_LAUNCHED(ctx);
             }
             ++sweeps;
@@ -232,11 +342,11 @@ extern "C" int tn_svd(tn_ctx* ctx, void* stream, int m, int n, const double* C, 
             converged = (*h_rot == 0);
         }
         if (!converged) {
-            tn_set_error("Jacobi SVD of a %d x %d matrix did not converge in %d sweeps", m, n, sweeps);
+            tn_set_error("Jacobi SVD of a %d x %d matrix (%d live vectors) did not converge in %d sweeps", m, n, nc, sweeps);
             return TN_ERR_NOCONV;
         }
     }
-    jacobi_finish_kernel<<<1, JT, 0, st>>>(E, ldw, a, ext, nc, transposed, U, ldu, S, Vt, ldvt, sv_tmp, rank_tmp);
+    jacobi_finish_kernel<<<1, JT, 0, st>>>(E, ldw, a, ext, nc, kfull, has_dead, meta, live_idx, U, ldu, S, Vt, ldvt, sv_tmp, rank_tmp);
     TN_LAUNCHED(ctx);
     if (h_sweeps) *h_sweeps = sweeps;
     return TN_OK;
@@ -246,7 +356,7 @@ extern "C" int tn_truncation_rank(tn_ctx* ctx, void* stream, const double* S, in
                                   double* h_discarded) {
     TN_REQUIRE(ctx != nullptr && k >= 1, "bad arguments");
     cudaStream_t st = as_stream(stream);
-    char* ws = (char*)tn_scratch(ctx, TN_SLOT_MISC, 64);
+    char* ws = (char*)tn_scratch(ctx, TN_SLOT_SORT, 64);
     if (!ws) return TN_ERR_NOMEM;
     int* d_keep = (int*)ws;
     double* d_disc = (double*)(ws + 8);

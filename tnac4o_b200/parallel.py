@@ -1,0 +1,60 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed).  The contraction path shards by independent units --
+instances (ground-state search) or samples (Gibbs sampling) -- so there is no data-path collective: ranks only agree
+on the partition and gather results at the end."""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def partition(n, world, rank):
+    """contiguous, balanced slice [lo, hi) of n units owned by `rank`"""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def world_info():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def max_over_ranks(seconds, device=None):
+    """timing rule of the bench contract: the slowest rank defines the step"""
+    rank, world = world_info()
+    if world == 1:
+        return float(seconds)
+    t = torch.tensor([seconds], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(values, device=None):
+    rank, world = world_info()
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.tolist()
+
+
+def gather_samples(energy, states):
+    """concatenate per-rank Gibbs samples in rank order (every rank receives the full arrays)"""
+    rank, world = world_info()
+    if world == 1:
+        return energy, states
+    parts = [None] * world
+    dist.all_gather_object(parts, (np.asarray(energy), np.asarray(states)))
+    return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts], axis=0)
+
+
+class UniformStream:
+    """The reference draws np.random.rand(M) once per site from the global numpy stream (tnac4o.py:617).  With the
+    samples sharded over ranks every rank draws the same M numbers (same seed) and keeps its slice, so the union of
+    the ranks' samples equals the single-GPU run."""
+
+    def __init__(self, M, rank=0, world=1):
+        self.M = M
+        self.lo, self.hi = partition(M, world, rank)
+
+    def draw(self):
+        return np.random.rand(self.M)[self.lo:self.hi]

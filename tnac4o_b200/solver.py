@@ -447,9 +447,15 @@ class tnac4o:
         self.logger.info('Elapsed search total: %.2f seconds', self.stats['seconds_rhoT'] + self.stats['seconds_search'])
         return self.energy
 
-    def gibbs_sampling(self, M=2 ** 10, graduate_truncation=True, Dmax=32, tolS=1e-15, tolV=1e-10, max_sweeps=20):
+    def gibbs_sampling(self, M=2 ** 10, graduate_truncation=True, Dmax=32, tolS=1e-15, tolV=1e-10, max_sweeps=20,
+                       shard=None):
         """Sample M configurations from the Boltzmann distribution (tnac4o.py:553-650).  One np.random.rand(M)
-        draw per site, in the reference's order, feeds the inverse-CDF kernel."""
+        draw per site, in the reference's order, feeds the inverse-CDF kernel.  ``shard=(rank, world)`` keeps only
+        this rank's slice of the M samples (every rank draws the same M uniforms, so the union over ranks equals the
+        single-GPU result); gather with :func:`tnac4o_b200.parallel.gather_samples`."""
+        from .parallel import UniformStream
+        stream = UniformStream(M, *(shard or (0, 1)))
+        M = stream.hi - stream.lo
         dev = self._dev()
         c = Context.get(dev)
         t0 = time.time()
@@ -478,7 +484,7 @@ class tnac4o:
                 A = self.rhoT[ny + 1].A[nx]
                 Dl, nd, Dr = A.shape
                 P = self._site_marginals(ws, cur, RRat, ny, nx, want_P='only')
-                uni = torch.from_numpy(np.random.rand(M)).to(dev)
+                uni = torch.from_numpy(np.ascontiguousarray(stream.draw())).to(dev)
                 check(lib.tn_sample(c.handle, c.stream, sites[nx].ref, M, nx, int(nx > 0), int(ny > 0), ptr(P), ptr(uni),
                                     ptr(cur.vind), cur.vind.stride(0), ptr(cur.Eng), ptr(parent), ptr(cell), ptr(Enew)))
                 check(lib.tn_materialise(c.handle, c.stream, sites[nx].ref, M, nx, ny * self.Nx + nx, nsites,

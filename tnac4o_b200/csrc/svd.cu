@@ -15,7 +15,11 @@
 // (mps.py:805-806), so vectors whose norm is below DEAD_FLOOR * ||C||_F (1e-3 * eps) are never rotated: they are
 // reported as exact zero singular values.  The orientation (rows or columns of C) with fewer live vectors is
 // orthogonalised -- for a triangular factor that is the graded side, typically 100-200 of 512.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -175,6 +179,141 @@ jacobi_round_kernel(double* __restrict__ E, int ldw, int a, int nc, int bsz, int
     if (lane == 0 && my_rot_total) atomicAdd(rot_count, my_rot_total);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Cluster-resident Jacobi: ALL vectors stay in the shared memory of one 8-CTA cluster for the whole iteration;
+// every vector is split along its length, CTA r holding slice r of the w-part and slice r of the j-part of every
+// vector.  One round of the tournament = (1) every CTA computes the partial 2x2 Gram of every pair on its slice and
+// sends it to the pair's owner CTA through DSMEM, (2) the owner sums the 8 partials in a fixed order, decides the
+// rotation and broadcasts (c, s), (3) every CTA rotates its slices.  Two cluster barriers per round and no kernel
+// launch or host read-back until convergence.
+constexpr int CLJ = 8;
+constexpr int CJ_MAXPAIRS = 256;                      // nc <= 512
+constexpr int CJ_MAXOWN = CJ_MAXPAIRS / CLJ;
+
+__global__ void __cluster_dims__(CLJ, 1, 1) __launch_bounds__(JT, 1)
+jacobi_cluster_kernel(double* __restrict__ E, int ldw, int a, int ext, int nc, int max_sweeps, double tol,
+                      const SvdMeta* __restrict__ meta, int* __restrict__ status /* [0] = sweeps, [1] = converged */) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    extern __shared__ __align__(16) double Sl[];      // [nc][ll]
+    __shared__ double part[CLJ][CJ_MAXOWN][3];
+    __shared__ double rot[CJ_MAXPAIRS][2];
+    __shared__ unsigned int cnt[2][CLJ];
+    __shared__ unsigned int myrot;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int aw = (a + CLJ - 1) / CLJ, ej = (ext + CLJ - 1) / CLJ, ll = aw + ej;
+    const int wlo = rank * aw, jlo = rank * ej;
+    const double floor2 = DEAD_FLOOR * DEAD_FLOOR * meta->fro2;
+    for (int64_t i = tid; i < (int64_t)nc * ll; i += JT) {
+        int k = (int)(i / ll), e = (int)(i % ll);
+        double v = 0.0;
+        if (e < aw) { if (wlo + e < a) v = E[(int64_t)k * ldw + wlo + e]; }
+        else { int f = e - aw; if (jlo + f < ext) v = E[(int64_t)k * ldw + a + jlo + f]; }
+        Sl[i] = v;
+    }
+    if (tid == 0) myrot = 0;
+    __syncthreads();
+    const int nce = nc + (nc & 1), r1 = nce - 1, half = nce / 2;
+    const int sub = lane & 7, grp = lane >> 3;                    // 8 lanes per pair, 4 pairs per warp
+    int sweep = 0, converged = 0;
+    for (; sweep < max_sweeps && r1 >= 1; ++sweep) {
+        for (int r = 0; r < r1; ++r) {
+            // ---- (1) partial Gram triples on my w-slice
+            for (int i0 = warp * 4; i0 < half; i0 += JW * 4) {
+                int i = i0 + grp;
+                double app = 0.0, aqq = 0.0, apq = 0.0;
+                int p = 0, q = 0;
+                bool valid = (i < half);
+                if (valid) {
+                    p = (r + i) % r1;
+                    q = (i == 0) ? r1 : (r + r1 - i) % r1;
+                    valid = (p < nc) && (q < nc);
+                }
+                if (valid) {
+                    const double* xp = Sl + (int64_t)p * ll;
+                    const double* xq = Sl + (int64_t)q * ll;
+                    for (int e = sub; e < aw; e += 8) {
+                        double u = xp[e], v = xq[e];
+                        app += u * u; aqq += v * v; apq += u * v;
+                    }
+                }
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) {
+                    app += __shfl_xor_sync(0xffffffffu, app, o);
+                    aqq += __shfl_xor_sync(0xffffffffu, aqq, o);
+                    apq += __shfl_xor_sync(0xffffffffu, apq, o);
+                }
+                if (sub == 0 && i < half) {
+                    double* dst = cluster.map_shared_rank(&part[rank][i / CLJ][0], i % CLJ);
+                    dst[0] = app; dst[1] = aqq; dst[2] = apq;
+                }
+            }
+            cluster.sync();
+            // ---- (2) owners decide the rotations and broadcast them
+            {
+                int i = tid * CLJ + rank;                          // pairs owned by this CTA: i % CLJ == rank
+                if (tid < CJ_MAXOWN && i < half) {
+                    double app = 0.0, aqq = 0.0, apq = 0.0;
+#pragma unroll
+                    for (int src = 0; src < CLJ; ++src) { app += part[src][tid][0]; aqq += part[src][tid][1]; apq += part[src][tid][2]; }
+                    double cs = 1.0, sn = 0.0;
+                    if (fabs(apq) > tol * sqrt(app) * sqrt(aqq) && app > floor2 && aqq > floor2) {
+                        double zeta = (aqq - app) / (2.0 * apq);
+                        double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                        cs = 1.0 / sqrt(1.0 + t * t);
+                        sn = cs * t;
+                        atomicAdd(&myrot, 1u);
+                    }
+#pragma unroll
+                    for (int dstc = 0; dstc < CLJ; ++dstc) {
+                        double* dst = cluster.map_shared_rank(&rot[i][0], dstc);
+                        dst[0] = cs; dst[1] = sn;
+                    }
+                }
+            }
+            cluster.sync();
+            // ---- (3) rotate my slices of every pair
+            for (int i0 = warp * 4; i0 < half; i0 += JW * 4) {
+                int i = i0 + grp;
+                if (i >= half) continue;
+                const double cs = rot[i][0], sn = rot[i][1];
+                if (sn == 0.0) continue;
+                int p = (r + i) % r1;
+                int q = (i == 0) ? r1 : (r + r1 - i) % r1;
+                double* xp = Sl + (int64_t)p * ll;
+                double* xq = Sl + (int64_t)q * ll;
+                for (int e = sub; e < ll; e += 8) {
+                    double u = xp[e], v = xq[e];
+                    xp[e] = cs * u - sn * v;
+                    xq[e] = sn * u + cs * v;
+                }
+            }
+            __syncthreads();
+        }
+        // ---- end of sweep: all CTAs learn the total number of rotations
+        const int buf = sweep & 1;
+        if (tid < CLJ) {
+            unsigned int* dst = cluster.map_shared_rank(&cnt[buf][rank], tid);
+            *dst = myrot;
+        }
+        cluster.sync();
+        unsigned int total = 0;
+#pragma unroll
+        for (int src = 0; src < CLJ; ++src) total += cnt[buf][src];
+        __syncthreads();
+        if (tid == 0) myrot = 0;
+        __syncthreads();
+        if (total == 0) { converged = 1; ++sweep; break; }
+    }
+    if (r1 < 1) converged = 1;
+    for (int64_t i = tid; i < (int64_t)nc * ll; i += JT) {
+        int k = (int)(i / ll), e = (int)(i % ll);
+        if (e < aw) { if (wlo + e < a) E[(int64_t)k * ldw + wlo + e] = Sl[i]; }
+        else { int f = e - aw; if (jlo + f < ext) E[(int64_t)k * ldw + a + jlo + f] = Sl[i]; }
+    }
+    if (rank == 0 && tid == 0) { status[0] = sweep; status[1] = converged; }
+}
+
 // norms -> S (sorted descending, dead vectors = exact zeros at the end), singular vectors with the sign rule of
 // mps.svd (mps.py:35-39).  U and Vt must be zero-filled by the caller.
 __global__ void __launch_bounds__(JT, 1)
@@ -266,9 +405,16 @@ extern "C" int tn_svd(tn_ctx* ctx, void* stream, int m, int n, const double* C, 
     // the side with fewer live vectors is chosen on the device
     const int force = (m < n) ? 1 : (m > n ? 0 : -1);
     const int a = (m < n) ? n : m;
-    // small problems: everything resident in one CTA, no deflation, no host read-back
-    const int ldw_full = a + (want_vectors ? kfull : 0);
-    const bool small = (size_t)kfull * ldw_full * sizeof(double) <= SMEM_LIMIT && kfull <= 512;
+    // small problems: everything resident in one CTA or one cluster without deflation -> no host read-back
+    const size_t CL_SMEM = 160 * 1024;
+    auto cluster_fits = [&](int nvec, int e) {
+        size_t ll = (size_t)ceil_div(a, CLJ) + (size_t)ceil_div(e, CLJ);
+        return nvec >= 2 && nvec <= 2 * CJ_MAXPAIRS && (size_t)nvec * ll * sizeof(double) <= CL_SMEM;
+    };
+    const int ext_full = want_vectors ? kfull : 0;
+    const int ldw_full = a + ext_full;
+    const bool tiny = kfull <= 32 && (size_t)kfull * ldw_full * sizeof(double) <= SMEM_LIMIT;
+    const bool small = tiny || cluster_fits(kfull, ext_full);
     svd_select_kernel<<<1, 256, 0, st>>>(norms2, m, n, force, small ? 0 : 1, meta, live_idx);
     TN_LAUNCHED(ctx);
     int nc = kfull;
@@ -311,19 +457,40 @@ extern "C" int tn_svd(tn_ctx* ctx, void* stream, int m, int n, const double* C, 
     if (cmax > 512) cmax = 512;
     const double tol = sqrt((double)a) * 2.220446049250313e-16;
     unsigned int* h_rot = (unsigned int*)ctx->pinned;
-    TN_CUDA(cudaFuncSetAttribute(jacobi_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
-    if (nc <= cmax) {
-        // resident: one CTA iterates to convergence
+    int* status = (int*)(rot + 2);
+    if (nc <= 32 && nc <= cmax) {
+        // tiny: one CTA iterates to convergence
         if (nc > 1) {
             int bsz = (nc + 1) / 2;
             size_t smem = (size_t)nc * ldw * sizeof(double);
+            TN_CUDA(cudaFuncSetAttribute(jacobi_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
             TN_CUDA(cudaMemsetAsync(rot, 0, sizeof(unsigned int), st));
             jacobi_round_kernel<<<1, JT, smem, st>>>(E, ldw, a, nc, bsz, 2, 0, MAX_SWEEPS, tol, meta, rot);
             TN_LAUNCHED(ctx);
         }
         sweeps = 1;
+    } else if (cluster_fits(nc, ext)) {
+        // cluster-resident: one launch, no host read-back inside the iteration
+        size_t ll = (size_t)ceil_div(a, CLJ) + (size_t)ceil_div(ext, CLJ);
+        size_t smem = (size_t)nc * ll * sizeof(double);
+        TN_CUDA(cudaFuncSetAttribute(jacobi_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CL_SMEM));
+        jacobi_cluster_kernel<<<CLJ, JT, smem, st>>>(E, ldw, a, ext, nc, MAX_SWEEPS, tol, meta, status);
+        TN_LAUNCHED(ctx);
+        sweeps = -1;
+        if (!small) {
+            // a host read-back already happened for this (large) matrix: also verify convergence
+            int* hs = (int*)((char*)ctx->pinned + 320);
+            TN_CUDA(cudaMemcpyAsync(hs, status, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+            TN_CUDA(cudaStreamSynchronize(st));
+            sweeps = hs[0];
+            if (!hs[1]) {
+                tn_set_error("Jacobi SVD of a %d x %d matrix (%d live vectors) did not converge in %d sweeps", m, n, nc, sweeps);
+                return TN_ERR_NOCONV;
+            }
+        }
     } else {
-        // smaller blocks than shared memory would allow keep more SMs busy and the inner sweeps short
+        // multi-block fall-back: block pairs per launch, one host read-back per sweep
+        TN_CUDA(cudaFuncSetAttribute(jacobi_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
         int bsz = cmax / 2;
         while (bsz > 8 && ceil_div(nc, bsz) < 16) bsz = (bsz + 1) / 2;
         int nblocks = ceil_div(nc, bsz);

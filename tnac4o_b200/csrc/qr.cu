@@ -1,9 +1,14 @@
 // Economic Householder QR with non-negative diag(R) -- replaces mps.qr (mps.py:43-59).
 //
-// Blocked compact-WY algorithm.  The panel (m x JB) is factored by ONE thread-block cluster of 8 CTAs: the
-// panel rows are split over the CTAs and kept in shared memory for the whole factorisation; the per-column
-// dot products are reduced across the cluster through distributed shared memory (one cluster.sync per
-// column).  Trailing updates and the accumulation of Q are DMMA GEMMs (gemm.cu).
+// Two-level blocked compact-WY algorithm.
+//   * Inner panel (m x 16): ONE thread-block cluster of 8 CTAs.  Every thread owns one matrix row in registers
+//     (16 doubles); the per-column dot products  x^T A[:, c]  of all 16 columns are reduced with a transposing
+//     warp butterfly (16 shuffle steps for 16 values), across warps through shared memory and across the 8 CTAs
+//     through distributed shared memory -- one cluster barrier per column.  The same reduction yields the Gram
+//     entries needed for the compact-WY factor T, so V, R and T come out of a single pass.
+//     (Panels taller than 8 x 1024 rows fall back to a shared-memory variant of the same scheme.)
+//   * The inner panels of an outer block (128 columns) update only that block; the block reflector
+//     (V_outer, T_outer) is then applied to the trailing matrix and, at the end, to Q with K = 128 DMMA GEMMs.
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -18,65 +23,202 @@ namespace {
 
 constexpr int CL = 8;          // CTAs per cluster
 constexpr int PT = 1024;       // threads per CTA
+constexpr int JB = 16;         // inner panel width
+constexpr int NB = 128;        // outer block width
 
-template <int JB>
+// ---------------------------------------------------------------------------------------------------------------
+// register-resident panel factorisation: rows_per <= PT
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(PT, 1)
-qr_panel_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, double* __restrict__ Vall, int ldv,
-                double* __restrict__ Tout) {
+qr_panel_reg_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, double* __restrict__ Vall, int ldv,
+                    double* __restrict__ Tout) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    __shared__ double red[PT / 32][JB];
+    __shared__ double cw[2][CL][JB];          // per-CTA partial dots, double-buffered by column parity
+    __shared__ double prow[2][JB];            // pivot row broadcast
+    __shared__ double sc[JB];                 // tau * v^T a_c
+    __shared__ double par[4];                 // beta, tau, scale
+    __shared__ double Ts[JB * JB];
+    __shared__ double gcol[JB];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m_rem = m - j0;
+    const int rows_per = (m_rem + CL - 1) / CL;
+    const int rel = rank * rows_per + tid;                      // my row, relative to j0
+    const bool have = (tid < rows_per) && (rel < m_rem);
+    double row[JB];
+#pragma unroll
+    for (int c = 0; c < JB; ++c) row[c] = (have && c < jb) ? A[(int64_t)(j0 + rel) * lda + j0 + c] : 0.0;
+    if (tid < JB * JB) Ts[tid] = 0.0;
+    __syncthreads();
+
+#pragma unroll
+    for (int j = 0; j < JB; ++j) {
+        if (j >= jb) break;
+        const int buf = j & 1;
+        const int owner = j / rows_per;
+        // ---- products with the rows strictly below the pivot
+        double v[JB];
+        const double x = (have && rel > j) ? row[j] : 0.0;
+#pragma unroll
+        for (int c = 0; c < JB; ++c) v[c] = x * row[c];
+        // transposing butterfly: after the 4 halving steps lane l holds the warp total of value idx(l)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            bool up = lane & 16;
+            double send = up ? v[k] : v[k + 8], keep = up ? v[k + 8] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            bool up = lane & 8;
+            double send = up ? v[k] : v[k + 4], keep = up ? v[k + 4] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            bool up = lane & 4;
+            double send = up ? v[k] : v[k + 2], keep = up ? v[k + 2] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        {
+            bool up = lane & 2;
+            double send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+            v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+        if ((lane & 1) == 0) {
+            int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            red[warp][idx] = v[0];
+        }
+        if (have && rel == j) {
+#pragma unroll
+            for (int c = 0; c < JB; ++c) gcol[c] = row[c];       // stage the pivot row (owner CTA only)
+        }
+        __syncthreads();
+        if (tid < JB * 32) {
+            int idx = tid >> 5;
+            double s = warp_sum(red[lane][idx]);
+            if (lane < CL) {
+                double* remote = cluster.map_shared_rank(&cw[buf][rank][idx], lane);
+                *remote = s;
+            }
+            if (rank == owner && lane >= 8 && lane < 8 + CL) {
+                double* remote = cluster.map_shared_rank(&prow[buf][idx], lane - 8);
+                *remote = gcol[idx];
+            }
+        }
+        cluster.sync();
+        // ---- reflector parameters, tau * v^T a_c for c > j, column j of T
+        if (tid < JB) {
+            double w = 0.0;
+#pragma unroll
+            for (int r = 0; r < CL; ++r) w += cw[buf][r][tid];
+            gcol[tid] = w;                                       // w_c = sum_{i > pivot} x_i a_ic
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const double wj = gcol[j], alpha = prow[buf][j];
+            double beta, tau, scale;
+            if (wj == 0.0) { beta = alpha; tau = 0.0; scale = 0.0; }
+            else {
+                beta = -copysign(sqrt(alpha * alpha + wj), alpha);
+                tau = (beta - alpha) / beta;
+                scale = 1.0 / (alpha - beta);
+            }
+            par[0] = beta; par[1] = tau; par[2] = scale;
+        }
+        __syncthreads();
+        const double beta = par[0], tau = par[1], scale = par[2];
+        if (tid < JB) {
+            // v^T a_c = a_c[pivot] + scale * w_c  (v = e_pivot + scale * x below the pivot)
+            double vta = prow[buf][tid] + scale * gcol[tid];
+            sc[tid] = tau * vta;
+            // T[0:j, j] = -tau * T[0:j, 0:j] * (V[:, 0:j]^T v_j); the Gram entries are vta for c < j
+            __syncwarp(0xffff);
+            if (tid < j) {
+                double s = 0.0;
+                for (int k = tid; k < j; ++k) s += Ts[tid * JB + k] * (prow[buf][k] + scale * gcol[k]);
+                Ts[tid * JB + j] = -tau * s;
+            }
+            if (tid == j) Ts[j * JB + j] = tau;
+        }
+        __syncthreads();
+        // ---- apply the reflector to my row
+        if (have) {
+            if (rel > j) {
+                const double vi = row[j] * scale;
+#pragma unroll
+                for (int c = 0; c < JB; ++c) if (c > j) row[c] -= vi * sc[c];
+                row[j] = vi;
+            } else if (rel == j) {
+#pragma unroll
+                for (int c = 0; c < JB; ++c) if (c > j) row[c] -= sc[c];
+                row[j] = beta;
+            }
+        }
+    }
+    // ---- write R (upper triangle of the pivot rows) and the explicit V
+    if (have) {
+#pragma unroll
+        for (int c = 0; c < JB; ++c) {
+            if (c < jb) {
+                if (rel <= c) A[(int64_t)(j0 + rel) * lda + j0 + c] = row[c];
+                Vall[(int64_t)(j0 + rel) * ldv + j0 + c] = (rel > c) ? row[c] : (rel == c ? 1.0 : 0.0);
+            }
+        }
+    }
+    __syncthreads();
+    if (rank == 0 && tid < JB * JB) Tout[tid] = Ts[tid];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// shared-memory variant for very tall panels (rows_per > PT); same algorithm, panel rows in dynamic shared memory
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(PT, 1)
+qr_panel_smem_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, double* __restrict__ Vall, int ldv,
+                     double* __restrict__ Tout) {
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     extern __shared__ __align__(16) double P[];          // [rows_per][JB]
-    __shared__ double cw[2][CL][JB];                      // per-CTA partial dots, double-buffered
-    __shared__ double prow[2][JB];                        // pivot row broadcast
+    __shared__ double cw[2][CL][JB];
+    __shared__ double prow[2][JB];
     __shared__ double red[PT / 32][JB];
     __shared__ double tau_s[JB];
-    __shared__ double Gpart[CL][JB * JB];                 // only rank 0's copy is used
+    __shared__ double Gpart[CL][JB * JB];
     __shared__ double Ts[JB * JB];
+    __shared__ double gred[PT];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = tid % JB, rg = tid / JB;
     constexpr int RG = PT / JB;
     const int m_rem = m - j0;
     const int rows_per = (m_rem + CL - 1) / CL;
-    const int r_begin = rank * rows_per;                          // relative to j0
+    const int r_begin = rank * rows_per;
     const int nloc = max(0, min(rows_per, m_rem - r_begin));
-
-    // load my rows of the panel
     for (int idx = tid; idx < nloc * JB; idx += PT) {
         int i = idx / JB, cc = idx % JB;
         P[idx] = (cc < jb) ? A[(int64_t)(j0 + r_begin + i) * lda + j0 + cc] : 0.0;
     }
     __syncthreads();
-
     for (int j = 0; j < jb; ++j) {
         const int buf = j & 1;
-        const int owner = j / rows_per;          // CTA that holds the pivot row (relative row j)
-        // ---- phase A: partial dots over rows strictly below the pivot
+        const int owner = j / rows_per;
         double acc = 0.0;
-        for (int i = rg; i < nloc; i += RG) {
+        for (int i = rg; i < nloc; i += RG)
             if (r_begin + i > j) acc += P[i * JB + j] * P[i * JB + c];
-        }
-        if (JB == 16) acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-        if (JB == 8) { acc += __shfl_xor_sync(0xffffffffu, acc, 16); acc += __shfl_xor_sync(0xffffffffu, acc, 8); }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
         if (lane < JB) red[warp][lane] = acc;
         __syncthreads();
         if (tid < JB) {
             double s = 0.0;
             for (int w = 0; w < PT / 32; ++w) s += red[w][tid];
-            for (int r = 0; r < CL; ++r) {
-                double* remote = cluster.map_shared_rank(&cw[buf][rank][tid], r);
-                *remote = s;
-            }
+            for (int r = 0; r < CL; ++r) *cluster.map_shared_rank(&cw[buf][rank][tid], r) = s;
             if (rank == owner) {
                 double pv = P[(j - r_begin) * JB + tid];
-                for (int r = 0; r < CL; ++r) {
-                    double* remote = cluster.map_shared_rank(&prow[buf][tid], r);
-                    *remote = pv;
-                }
+                for (int r = 0; r < CL; ++r) *cluster.map_shared_rank(&prow[buf][tid], r) = pv;
             }
         }
         cluster.sync();
-        // ---- phase B: reflector parameters (every thread, identical arithmetic)
         double wj = 0.0, wc = 0.0;
 #pragma unroll
         for (int r = 0; r < CL; ++r) { wj += cw[buf][r][j]; wc += cw[buf][r][c]; }
@@ -88,15 +230,11 @@ qr_panel_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, double* 
             tau = (beta - alpha) / beta;
             scale = 1.0 / (alpha - beta);
         }
-        const double sc = tau * (prow[buf][c] + scale * wc);     // tau * v^T a_c
-        // ---- phase C: apply to the remaining panel columns
+        const double scv = tau * (prow[buf][c] + scale * wc);
         for (int i = rg; i < nloc; i += RG) {
             int rel = r_begin + i;
-            if (rel > j) {
-                if (c > j) P[i * JB + c] -= (P[i * JB + j] * scale) * sc;
-            } else if (rel == j) {
-                if (c > j) P[i * JB + c] -= sc;
-            }
+            if (rel > j) { if (c > j) P[i * JB + c] -= (P[i * JB + j] * scale) * scv; }
+            else if (rel == j) { if (c > j) P[i * JB + c] -= scv; }
         }
         __syncthreads();
         if (c == j) {
@@ -109,40 +247,31 @@ qr_panel_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, double* 
         }
         __syncthreads();
     }
-
-    // ---- write R rows back to A, convert the shared panel to explicit V, store V
     for (int idx = tid; idx < nloc * JB; idx += PT) {
         int i = idx / JB, cc = idx % JB;
         int rel = r_begin + i;
         double x = P[idx];
         if (cc < jb) {
-            if (rel <= cc) A[(int64_t)(j0 + rel) * lda + j0 + cc] = x;      // upper triangle incl. diagonal = R
+            if (rel <= cc) A[(int64_t)(j0 + rel) * lda + j0 + cc] = x;
             double v = (rel > cc) ? x : (rel == cc ? 1.0 : 0.0);
             P[idx] = v;
             Vall[(int64_t)(j0 + rel) * ldv + j0 + cc] = v;
-        } else {
-            P[idx] = 0.0;
-        }
+        } else P[idx] = 0.0;
     }
     __syncthreads();
-    // ---- Gram of V for the T factor: G[a][b] = sum_rows V[.,a] V[.,b]
     {
         constexpr int NP = JB * JB;
-        constexpr int SL = PT / NP;                      // row slices per (a,b) pair
+        constexpr int SL = PT / NP;
         int pair = tid % NP, sl = tid / NP;
         int a = pair / JB, b = pair % JB;
         double g = 0.0;
-        if (sl < SL)
-            for (int i = sl; i < nloc; i += SL) g += P[i * JB + a] * P[i * JB + b];
-        // reduce the SL slices through shared memory (reuse red as scratch is too small -> use Ts stages)
-        __shared__ double gred[PT];
+        for (int i = sl; i < nloc; i += SL) g += P[i * JB + a] * P[i * JB + b];
         gred[tid] = g;
         __syncthreads();
         if (tid < NP) {
             double s = 0.0;
             for (int q = 0; q < SL; ++q) s += gred[q * NP + tid];
-            double* remote = cluster.map_shared_rank(&Gpart[rank][tid], 0);
-            *remote = s;
+            *cluster.map_shared_rank(&Gpart[rank][tid], 0) = s;
         }
     }
     cluster.sync();
@@ -151,12 +280,11 @@ qr_panel_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, double* 
         if (tid < NP) {
             double s = 0.0;
             for (int r = 0; r < CL; ++r) s += Gpart[r][tid];
-            Gpart[0][tid] = s;            // own slot r = 0 is summed first, safe to overwrite after the loop
+            Gpart[0][tid] = s;
             Ts[tid] = 0.0;
         }
         __syncthreads();
         if (tid == 0) {
-            // forward columnwise dlarft: T[j][j] = tau_j, T[0:j, j] = -tau_j * T[0:j,0:j] * G[0:j, j]
             for (int j = 0; j < jb; ++j) {
                 for (int i = 0; i < j; ++i) {
                     double s = 0.0;
@@ -169,6 +297,49 @@ qr_panel_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, double* 
         __syncthreads();
         if (tid < NP) Tout[tid] = Ts[tid];
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// T of an outer block from the inner T_p and the Gram matrix G = V^T V of the block's reflectors:
+//   T[0:J, Jblk] = -T[0:J, 0:J] * G[0:J, Jblk] * T_Jblk        (merging compact-WY factors)
+__global__ void __launch_bounds__(256, 1)
+build_outer_T_kernel(const double* __restrict__ G, int ldg, const double* __restrict__ Tin, int nbw, double* __restrict__ Tout) {
+    extern __shared__ __align__(16) double sm[];
+    double* T = sm;                 // [NB][NB]
+    double* Y = sm + NB * NB;       // [NB][JB]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < NB * NB; i += 256) T[i] = 0.0;
+    __syncthreads();
+    const int nblk = (nbw + JB - 1) / JB;
+    for (int q = 0; q < nblk; ++q) {
+        const int J = q * JB, jb = min(JB, nbw - J);
+        const double* Tq = Tin + (size_t)q * JB * JB;
+        // diagonal block
+        for (int i = tid; i < JB * JB; i += 256) {
+            int r = i / JB, c = i % JB;
+            if (r < jb && c < jb) T[(J + r) * NB + J + c] = Tq[r * JB + c];
+        }
+        // Y = T[0:J, 0:J] * G[0:J, Jblk]
+        for (int i = tid; i < J * JB; i += 256) {
+            int r = i / JB, c = i % JB;
+            double s = 0.0;
+            if (c < jb)
+                for (int k = r; k < J; ++k) s += T[r * NB + k] * G[(size_t)k * ldg + J + c];
+            Y[i] = s;
+        }
+        __syncthreads();
+        // T[0:J, Jblk] = -Y * T_q
+        for (int i = tid; i < J * JB; i += 256) {
+            int r = i / JB, c = i % JB;
+            if (c < jb) {
+                double s = 0.0;
+                for (int k = 0; k <= c; ++k) s += Y[r * JB + k] * Tq[k * JB + c];
+                T[r * NB + J + c] = -s;
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < NB * NB; i += 256) Tout[i] = T[i];
 }
 
 __global__ void set_identity_kernel(double* Q, int ldq, int m, int k) {
@@ -204,65 +375,30 @@ __global__ void qr_finish_kernel(const double* __restrict__ A, int lda, int m, i
     }
 }
 
-template <int JB>
-int qr_impl(tn_ctx* ctx, cudaStream_t st, int m, int n, double* A, int lda, double* Q, int ldq, double* R, int ldr,
-            unsigned long long* maxabs_bits) {
-    const int k = min(m, n);
-    const int npan = ceil_div(k, JB);
-    const int wcols = max(n, k);
-    size_t need = ((size_t)m * k + (size_t)npan * JB * JB + 2 * (size_t)JB * wcols) * sizeof(double);
-    double* ws = (double*)tn_scratch(ctx, TN_SLOT_QR, need);
-    if (!ws) return TN_ERR_NOMEM;
-    double* Vall = ws;
-    double* Tall = Vall + (size_t)m * k;
-    double* W = Tall + (size_t)npan * JB * JB;
-    double* W2 = W + (size_t)JB * wcols;
-
-    auto kern = qr_panel_kernel<JB>;
-    const int rows_per_max = ceil_div(m, CL);
-    size_t smem = (size_t)rows_per_max * JB * sizeof(double);
-    TN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-
-    for (int p = 0; p < npan; ++p) {
-        int j0 = p * JB, jb = min(JB, k - j0);
-        kern<<<CL, PT, smem, st>>>(A, lda, m, j0, jb, Vall, k, Tall + (size_t)p * JB * JB);
-        TN_LAUNCHED(ctx);
-        int n2 = n - (j0 + jb);
-        if (n2 > 0) {
-            int mr = m - j0;
-            const double* V = Vall + (size_t)j0 * k + j0;
-            double* A2 = A + (size_t)j0 * lda + j0 + jb;
-            int rc;
-            if ((rc = tn_gemm_impl(ctx, st, 1, 0, jb, n2, mr, 1.0, V, k, 0, A2, lda, 0, 0.0, W, n2, 0, 1))) return rc;
-            if ((rc = tn_gemm_impl(ctx, st, 1, 0, jb, n2, jb, 1.0, Tall + (size_t)p * JB * JB, JB, 0, W, n2, 0, 0.0, W2, n2, 0, 1))) return rc;
-            if ((rc = tn_gemm_impl(ctx, st, 0, 0, mr, n2, jb, -1.0, V, k, 0, W2, n2, 0, 1.0, A2, lda, 0, 1))) return rc;
+int launch_panel(tn_ctx* ctx, cudaStream_t st, double* A, int lda, int m, int j0, int jb, double* Vall, int ldv, double* T) {
+    const int rows_per = ceil_div(m - j0, CL);
+    if (rows_per <= PT) {
+        qr_panel_reg_kernel<<<CL, PT, 0, st>>>(A, lda, m, j0, jb, Vall, ldv, T);
+    } else {
+        size_t smem = (size_t)rows_per * JB * sizeof(double);
+        if (smem > 150 * 1024) {
+            tn_set_error("QR panel of %d rows is too tall for the cluster panel kernels", m - j0);
+            return TN_ERR_ARG;
         }
+        TN_CUDA(cudaFuncSetAttribute(qr_panel_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        qr_panel_smem_kernel<<<CL, PT, smem, st>>>(A, lda, m, j0, jb, Vall, ldv, T);
     }
-    // accumulate Q = H_1 ... H_p [I; 0]
-    {
-        int64_t total = (int64_t)m * k;
-        int blocks = (int)((total + 255) / 256 < 8 * ctx->sm_count ? (total + 255) / 256 : 8 * ctx->sm_count);
-        set_identity_kernel<<<blocks, 256, 0, st>>>(Q, ldq, m, k);
-        TN_LAUNCHED(ctx);
-    }
-    for (int p = npan - 1; p >= 0; --p) {
-        int j0 = p * JB, jb = min(JB, k - j0);
-        int mr = m - j0, kc = k - j0;
-        const double* V = Vall + (size_t)j0 * k + j0;
-        double* Q2 = Q + (size_t)j0 * ldq + j0;
-        int rc;
-        if ((rc = tn_gemm_impl(ctx, st, 1, 0, jb, kc, mr, 1.0, V, k, 0, Q2, ldq, 0, 0.0, W, kc, 0, 1))) return rc;
-        if ((rc = tn_gemm_impl(ctx, st, 0, 0, jb, kc, jb, 1.0, Tall + (size_t)p * JB * JB, JB, 0, W, kc, 0, 0.0, W2, kc, 0, 1))) return rc;
-        if ((rc = tn_gemm_impl(ctx, st, 0, 0, mr, kc, jb, -1.0, V, k, 0, W2, kc, 0, 1.0, Q2, ldq, 0, 1))) return rc;
-    }
-    if (maxabs_bits) TN_CUDA(cudaMemsetAsync(maxabs_bits, 0, sizeof(unsigned long long), st));
-    {
-        int64_t total = (int64_t)k * n + (int64_t)m * k;
-        int blocks = (int)((total + 255) / 256 < 8 * ctx->sm_count ? (total + 255) / 256 : 8 * ctx->sm_count);
-        qr_finish_kernel<<<blocks, 256, 0, st>>>(A, lda, m, n, k, Q, ldq, R, ldr, maxabs_bits);
-        TN_LAUNCHED(ctx);
-    }
+    TN_LAUNCHED(ctx);
     return TN_OK;
+}
+
+// C2 <- (I - V T' V^T) C2 with T' = T or T^T; V (mr x kb, ldv), T (kb x kb, ldt), C2 (mr x nc, ldc); W, W2 scratch (kb x nc)
+int apply_block(tn_ctx* ctx, cudaStream_t st, int mr, int kb, int nc, const double* V, int ldv, const double* T, int ldt,
+                int transT, double* C2, int ldc, double* W, double* W2) {
+    int rc;
+    if ((rc = tn_gemm_impl(ctx, st, 1, 0, kb, nc, mr, 1.0, V, ldv, 0, C2, ldc, 0, 0.0, W, nc, 0, 1))) return rc;
+    if ((rc = tn_gemm_impl(ctx, st, transT, 0, kb, nc, kb, 1.0, T, ldt, 0, W, nc, 0, 0.0, W2, nc, 0, 1))) return rc;
+    return tn_gemm_impl(ctx, st, 0, 0, mr, nc, kb, -1.0, V, ldv, 0, W2, nc, 0, 1.0, C2, ldc, 0, 1);
 }
 
 }  // namespace
@@ -273,9 +409,73 @@ extern "C" int tn_qr_pos(tn_ctx* ctx, void* stream, int m, int n, double* A, int
     TN_REQUIRE(m >= 1 && n >= 1, "empty matrix");
     TN_REQUIRE(lda >= n && ldq >= (m < n ? m : n) && ldr >= n, "bad leading dimension");
     cudaStream_t st = as_stream(stream);
-    const int rows_per = ceil_div(m, CL);
-    if ((size_t)rows_per * 16 * sizeof(double) <= 160 * 1024)
-        return qr_impl<16>(ctx, st, m, n, A, lda, Q, ldq, R, ldr, maxabs_bits);
-    TN_REQUIRE((size_t)rows_per * 8 * sizeof(double) <= 160 * 1024, "matrix too tall for the shared-memory panel");
-    return qr_impl<8>(ctx, st, m, n, A, lda, Q, ldq, R, ldr, maxabs_bits);
+    const int k = m < n ? m : n;
+    const int nouter = ceil_div(k, NB);
+    const int wcols = n > k ? n : k;
+    // scratch: V (m x k) | inner T's (JB x JB each) | outer T's (NB x NB each) | G (NB x NB) | W, W2 (NB x wcols)
+    const int npan = ceil_div(k, JB);
+    size_t need = ((size_t)m * k + (size_t)npan * JB * JB + (size_t)nouter * NB * NB + (size_t)NB * NB + 2 * (size_t)NB * wcols) * sizeof(double);
+    double* ws = (double*)tn_scratch(ctx, TN_SLOT_QR, need);
+    if (!ws) return TN_ERR_NOMEM;
+    double* Vall = ws;
+    double* Tin = Vall + (size_t)m * k;
+    double* Tout = Tin + (size_t)npan * JB * JB;
+    double* G = Tout + (size_t)nouter * NB * NB;
+    double* W = G + (size_t)NB * NB;
+    double* W2 = W + (size_t)NB * wcols;
+    const size_t tsmem = ((size_t)NB * NB + (size_t)NB * JB) * sizeof(double);
+    TN_CUDA(cudaFuncSetAttribute(build_outer_T_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+    int rc;
+    for (int ob = 0; ob < nouter; ++ob) {
+        const int J0 = ob * NB, nbw = (k - J0) < NB ? (k - J0) : NB;
+        const int pan0 = J0 / JB;
+        for (int jj = J0; jj < J0 + nbw; jj += JB) {
+            const int jb = (J0 + nbw - jj) < JB ? (J0 + nbw - jj) : JB;
+            double* Tp = Tin + (size_t)(jj / JB) * JB * JB;
+            if ((rc = launch_panel(ctx, st, A, lda, m, jj, jb, Vall, k, Tp))) return rc;
+            const int rem = J0 + nbw - (jj + jb);       // remaining columns of this outer block
+            if (rem > 0) {
+                if ((rc = apply_block(ctx, st, m - jj, jb, rem, Vall + (size_t)jj * k + jj, k, Tp, JB, 1,
+                                      A + (size_t)jj * lda + jj + jb, lda, W, W2))) return rc;
+            }
+        }
+        double* To = Tout + (size_t)ob * NB * NB;
+        const double* Vo = Vall + (size_t)J0 * k + J0;
+        const int mr = m - J0;
+        if (nbw > JB) {
+            // block reflector of the whole outer block
+            if ((rc = tn_gemm_impl(ctx, st, 1, 0, nbw, nbw, mr, 1.0, Vo, k, 0, Vo, k, 0, 0.0, G, NB, 0, 1))) return rc;
+            build_outer_T_kernel<<<1, 256, tsmem, st>>>(G, NB, Tin + (size_t)pan0 * JB * JB, nbw, To);
+            TN_LAUNCHED(ctx);
+        } else {
+            // single inner panel: T_outer = T_inner (embedded with leading dimension NB)
+            TN_CUDA(cudaMemsetAsync(To, 0, (size_t)NB * NB * sizeof(double), st));
+            TN_CUDA(cudaMemcpy2DAsync(To, NB * sizeof(double), Tin + (size_t)pan0 * JB * JB, JB * sizeof(double),
+                                      JB * sizeof(double), JB, cudaMemcpyDeviceToDevice, st));
+        }
+        const int n2 = n - (J0 + nbw);
+        if (n2 > 0) {
+            if ((rc = apply_block(ctx, st, mr, nbw, n2, Vo, k, To, NB, 1, A + (size_t)J0 * lda + J0 + nbw, lda, W, W2))) return rc;
+        }
+    }
+    // accumulate Q = H_1 ... H_p [I; 0], outer blocks backwards
+    {
+        int64_t total = (int64_t)m * k;
+        int blocks = (int)((total + 255) / 256 < 8 * ctx->sm_count ? (total + 255) / 256 : 8 * ctx->sm_count);
+        set_identity_kernel<<<blocks, 256, 0, st>>>(Q, ldq, m, k);
+        TN_LAUNCHED(ctx);
+    }
+    for (int ob = nouter - 1; ob >= 0; --ob) {
+        const int J0 = ob * NB, nbw = (k - J0) < NB ? (k - J0) : NB;
+        if ((rc = apply_block(ctx, st, m - J0, nbw, k - J0, Vall + (size_t)J0 * k + J0, k, Tout + (size_t)ob * NB * NB, NB, 0,
+                              Q + (size_t)J0 * ldq + J0, ldq, W, W2))) return rc;
+    }
+    if (maxabs_bits) TN_CUDA(cudaMemsetAsync(maxabs_bits, 0, sizeof(unsigned long long), st));
+    {
+        int64_t total = (int64_t)k * n + (int64_t)m * k;
+        int blocks = (int)((total + 255) / 256 < 8 * ctx->sm_count ? (total + 255) / 256 : 8 * ctx->sm_count);
+        qr_finish_kernel<<<blocks, 256, 0, st>>>(A, lda, m, n, k, Q, ldq, R, ldr, maxabs_bits);
+        TN_LAUNCHED(ctx);
+    }
+    return TN_OK;
 }

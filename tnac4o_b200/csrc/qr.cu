@@ -429,6 +429,8 @@ extern "C" int tn_qr_pos(tn_ctx* ctx, void* stream, int m, int n, double* A, int
     for (int ob = 0; ob < nouter; ++ob) {
         const int J0 = ob * NB, nbw = (k - J0) < NB ? (k - J0) : NB;
         const int pan0 = J0 / JB;
+        // V_outer has zeros above the diagonal of the block: the panel kernels only write rows >= their own first row
+        TN_CUDA(cudaMemset2DAsync(Vall + (size_t)J0 * k + J0, (size_t)k * sizeof(double), 0, (size_t)nbw * sizeof(double), nbw, st));
         for (int jj = J0; jj < J0 + nbw; jj += JB) {
             const int jb = (J0 + nbw - jj) < JB ? (J0 + nbw - jj) : JB;
             double* Tp = Tin + (size_t)(jj / JB) * JB * JB;

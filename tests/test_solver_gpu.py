@@ -191,3 +191,56 @@ def test_config4_L2048_M1024():
     # L=2048 truncations are ill-conditioned: the reference against itself (gesdd vs gesvd, or two CPUs) moves rhoT by
     # 1 - fidelity ~ 4e-12 and the accumulated log2 P by ~1e-6 relative
     np.testing.assert_allclose(ins.probability, z['gs_probability'], rtol=5e-6)
+
+
+def test_j124_degeneracy_counting():
+    """J124 C8 #1 (examples/test_examples.py:139-147): E = -2309 exactly, degeneracy 1152 -- exercises the merge rule"""
+    z = golden('instances.npz')
+    J = [[int(a) - 1, int(b) - 1, float(c)] for a, b, c in zip(z['J124_C8_001_i'], z['J124_C8_001_j'], z['J124_C8_001_v'])]
+    import tnac4o_b200
+    ins = tnac4o_b200.tnac4o(mode='Ising', Nx=8, Ny=8, Nc=8, J=J, beta=0.75)
+    ins.precondition(mode='balancing')
+    ins.search_ground_state(M=2 ** 12, relative_P_cutoff=1e-8, Dmax=8)
+    assert abs(ins.energy[0] - (-2309)) < 1e-12
+    assert int(ins.degeneracy) == 1152
+    ref = golden('ref_j124.npz')
+    assert abs(ins.energy[0] - ref['gs_energy'][0]) < 1e-12 and int(ref['gs_degeneracy']) == 1152
+    E = tnac4o_b200.energy_Jij(J, ins.binary_states())
+    assert abs(E[0] + 2309) < 1e-9
+
+
+def test_config3_L1152_spectrum_and_decode():
+    """BASELINE config 3: low-energy spectrum of L=1152 #1 (ee=1, dE=1, Dmax=32), decoded: 545 966 states in the
+    reference run; energies of all decoded states re-checked with the CSR energy kernel"""
+    import tnac4o_b200
+    z = golden('ref_l1152.npz')
+    J = droplet_couplings(1152)
+    ins = make(J, L=1152)
+    ins.search_low_energy_spectrum(excitations_encoding=1, M=1024, relative_P_cutoff=1e-8, Dmax=32, max_dEng=1.0)
+    assert abs(ins.energy[0] - z['gs_energy'][0]) < 1e-9
+    assert int(ins.degeneracy) == int(z['gs_degeneracy'])
+    e0 = ins.energy[0]
+    ins.decode_low_energy_states(max_dEng=1.0, max_states=2 ** 20)
+    n_ref = int(z['n_states'])
+    assert abs(len(ins.energy) - n_ref) <= 0.001 * n_ref              # borderline branches may differ
+    vals, counts = np.unique(np.round((ins.energy - e0) * 75).astype(np.int64), return_counts=True)
+    ref_levels = dict(zip(z['level_75dE'].tolist(), z['level_count'].tolist()))
+    low = [(v, c) for v, c in zip(vals.tolist(), counts.tolist()) if v <= 40]
+    assert all(ref_levels.get(v) == c for v, c in low), (low[:10], [(k, ref_levels[k]) for k in sorted(ref_levels)[:10]])
+    E = tnac4o_b200.energy_Jij(J, ins.binary_states())
+    assert np.max(np.abs(E - ins.energy)) < 1e-6
+    assert len(np.unique(ins.states, axis=0)) == len(ins.states)        # all decoded states are distinct
+
+
+def test_config5_gibbs_L2048_reduced():
+    """BASELINE config 5 at reduced sample count: beta = 1, L = 2048; sampled energies equal energy_Jij of the states"""
+    import tnac4o_b200
+    J = droplet_couplings(2048)
+    ins = make(J, L=2048, beta=1)
+    np.random.seed(1)
+    ins.gibbs_sampling(M=2000, Dmax=32)
+    assert ins.states.shape == (2000, 256) and ins.negative_probability > -1e-6
+    E = tnac4o_b200.energy_Jij(J, ins.binary_states())
+    assert np.max(np.abs(E - ins.energy)) < 1e-6
+    assert len(np.unique(ins.states, axis=0)) > 1900
+    assert -3200 < ins.energy.mean() < -2900                               # reference run: <E> = -3038.85 at M = 10^3

@@ -4,11 +4,15 @@
     python bench.py --gpus N --steps K --warmup W            # the sm_100a path (one process per GPU under torchrun)
     python bench.py --impl reference --gpus N --steps K --warmup W   # the reference algorithm (numpy port) on the host cores
 
-A step is one pass of the hot path over one instance: boundary-MPS build (_setup_rhoT) + branch-and-bound
-(search_ground_state) at M = 2^10, Dmax = 32, beta = 3, relative_P_cutoff = 1e-8, no preconditioning
-(BASELINE.json config 4, the M = 2^10 variant the north star quotes its target on).  Rank 0 solves droplet
-instance 001 (checked against the reference's golden energy); other ranks solve synthetic instances with the
-same coupling pattern (weak scaling: independent instances, no data-path collective -- DESIGN.md section (e)).
+A step is one pass of the hot path over one batch of `--batch` independent instances per GPU: for each instance the
+boundary-MPS build (_setup_rhoT) + branch-and-bound (search_ground_state) at M = 2^10, Dmax = 32, beta = 3,
+relative_P_cutoff = 1e-8, no preconditioning (BASELINE.json config 4, the M = 2^10 variant the north star quotes its
+target on).  The instances of a batch run concurrently, one host thread and one CUDA stream each: a single
+boundary-MPS build is a latency-bound chain that keeps 8 of 148 SMs busy, so instance-level concurrency is how one
+GPU is filled.  Instance 0 of rank 0 is droplet instance 001 (checked against the reference's golden energy); all
+others are synthetic instances on the same coupling pattern (weak scaling: independent instances, no data-path
+collective -- DESIGN.md section 6).  `value` is whole-job seconds per instance; the single-instance latency is
+reported next to it.
 """
 import argparse
 import json
@@ -135,23 +139,39 @@ def run_gpu(args):
     import tnac4o_b200
     from tnac4o_b200 import ops, mps
 
-    J = instance_couplings(rank)
+    from tnac4o_b200 import parallel
+    B = args.batch
+    J = instance_couplings(rank * B)
     t_prep = time.time()
-    ins = tnac4o_b200.tnac4o(mode='Ising', Nx=CFG['Nx'], Ny=CFG['Ny'], Nc=CFG['Nc'], J=J, beta=CFG['beta'], device=dev)
-    t_prep = time.time() - t_prep
-    ins._site_tables()                                    # inputs resident in HBM before the timed region
+    inss = [tnac4o_b200.tnac4o(mode='Ising', Nx=CFG['Nx'], Ny=CFG['Ny'], Nc=CFG['Nc'], J=instance_couplings(rank * B + i),
+                               beta=CFG['beta'], device=dev) for i in range(B)]
+    t_prep = (time.time() - t_prep) / B
+    ins = inss[0]
+    for x in inss:
+        x._site_tables()                                  # inputs resident in HBM before the timed region
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
-    def step(e2e):
+    def solve(x):
+        return lambda: x.search_ground_state(M=CFG['M'], relative_P_cutoff=CFG['relative_P_cutoff'], Dmax=CFG['Dmax'])
+
+    def step(e2e, which=None):
+        which = inss if which is None else which
         if e2e:
-            ins._sites = None                             # host tables -> HBM inside the timed region
+            for x in which:
+                x._sites = None                           # host tables -> HBM inside the timed region
         flush.fill_(1)
+        torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ins.search_ground_state(M=CFG['M'], relative_P_cutoff=CFG['relative_P_cutoff'], Dmax=CFG['Dmax'])
+        if len(which) == 1:
+            solve(which[0])()
+        else:
+            parallel.run_concurrently([solve(x) for x in which], device=dev)
+        torch.cuda.synchronize(dev)
         e1.record(); e1.synchronize()
-        return e0.elapsed_time(e1) * 1e-3, time.perf_counter() - t0, dict(ins.stats)
+        st = {k: float(np.sum([x.stats[k] for x in which])) for k in ('marginals', 'seconds_rhoT', 'seconds_search')}
+        return e0.elapsed_time(e1) * 1e-3, time.perf_counter() - t0, st
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -181,26 +201,32 @@ def run_gpu(args):
         step(True)
     barrier()
     total_e2e = time.perf_counter() - t_begin
-    h2d = sum(t.numel() * t.element_size() for row in ins._sites for s in row
-              for t in (s.Wlu, s.WtrU, s.Wmpo, s.dmap, s.rmap, s.Es, s.Esl, s.Esu))
-    d2h = ins.energy.nbytes + ins.states.nbytes + ins.probability.nbytes + 3 * 8
+    h2d = B * sum(t.numel() * t.element_size() for row in ins._sites for s in row
+                  for t in (s.Wlu, s.WtrU, s.Wmpo, s.dmap, s.rmap, s.Es, s.Esl, s.Esu))
+    d2h = B * (ins.energy.nbytes + ins.states.nbytes + ins.probability.nbytes + 3 * 8)
+    # single-instance latency (one stream), two extra steps outside the timed region
+    lat_runs = [step(False, [ins]) for _ in range(2)]
+    lat = min(r[0] for r in lat_runs)
+    lat_stats = lat_runs[-1][2]
 
     if world > 1:
         t = torch.tensor([total, total_e2e], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total, total_e2e = t.tolist()
-        cnt = torch.tensor([launches, sum(s['marginals'] for s in stats), sum(s['seconds_search'] for s in stats)],
+        cnt = torch.tensor([launches, sum(s['marginals'] for s in stats), sum(s['seconds_search'] for s in stats) / B],
                            dtype=torch.float64, device=dev)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         launches_all, marg_all, search_s_all = cnt.tolist()
     else:
         launches_all, marg_all = launches, sum(s['marginals'] for s in stats)
-        search_s_all = sum(s['seconds_search'] for s in stats)
+        search_s_all = sum(s['seconds_search'] for s in stats) / B
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    instances = args.steps * world
+    instances = args.steps * world * B
+    frac_search = (sum(s['seconds_search'] for s in stats) /
+                   max(1e-30, sum(s['seconds_rhoT'] + s['seconds_search'] for s in stats)))
     value = total / instances
     # ---- parity guard on the timed workload: golden energy of instance 001 (groundstates_otn2d.txt:1)
     from conftest import droplet_golden
@@ -210,7 +236,7 @@ def run_gpu(args):
     # ---- roofline pass (one extra, instrumented step; not part of the timed region)
     peak = fp64_peak(torch, dev)
     log, raw = instrument_gemm(ops, torch)
-    step(False)
+    step(False, [ins])
     torch.cuda.synchronize(dev)
     ops.gemm = raw
     flops = sum(f for f, _, _ in log)
@@ -228,10 +254,13 @@ def run_gpu(args):
            'ms_per_step': 1e3 * total / args.steps, 'higher_is_better': False, 'scaling': 'weak', 'vs_baseline': None,
            'dtype': 'f64', 'data': 'droplet instance 001 (rank 0) + synthetic couplings on the same chimera pattern (other ranks)',
            'config': {'workload': 'e01 ground-state search L=2048 (16x16x8 chimera), M=2^10, Dmax=32, beta=3, P_cutoff=1e-8, no preconditioning',
+                      'batch_per_gpu': B, 'concurrency': 'one host thread + one CUDA stream per instance',
                       'l2': 'flushed between steps (256 MiB write)', 'parity_energy_matches_golden': parity_ok},
-           'seconds_rhoT': float(np.mean([s['seconds_rhoT'] for s in stats])),
-           'seconds_search': float(np.mean([s['seconds_search'] for s in stats])),
-           'branch_marginals_per_s': marg_all / search_s_all * world if search_s_all else None,
+           'latency_seconds_single_instance': lat,
+           'seconds_rhoT_per_instance_in_batch': float(np.mean([s['seconds_rhoT'] for s in stats])) / B,
+           'seconds_search_per_instance_in_batch': float(np.mean([s['seconds_search'] for s in stats])) / B,
+           'branch_marginals_per_s': marg_all / (total * frac_search) if frac_search else None,
+           'branch_marginals_per_s_single_stream': lat_stats['marginals'] / lat_stats['seconds_search'],
            'device_seconds_per_step_rank0': float(np.mean(dev_s)),
            'host_model_prep_seconds': t_prep,
            'e2e': {'value': total_e2e / instances, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
@@ -364,6 +393,7 @@ if __name__ == '__main__':
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=8, help='independent instances solved concurrently per GPU')
     a = ap.parse_args()
     if a.impl == 'reference':
         run_reference(a)

@@ -5,6 +5,7 @@ CUDA device, raises.  torch is used only for device memory and streams.
 """
 import ctypes
 import os
+import threading
 from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_int64, c_void_p
 
 import torch
@@ -76,9 +77,11 @@ def check(rc):
 
 
 class Context:
-    """One library context per CUDA device (tn_create / tn_destroy)."""
+    """One library context (tn_create / tn_destroy) per CUDA device and host thread: a context owns its scratch
+    memory, so concurrent solver instances -- one host thread and one CUDA stream each -- never share one."""
 
-    _by_device = {}
+    _by_key = {}
+    _lock = threading.Lock()
 
     def __init__(self, device_index):
         if not torch.cuda.is_available():
@@ -96,9 +99,20 @@ class Context:
             index = torch.cuda.current_device() if torch.cuda.is_available() else 0
         else:
             index = torch.device(device).index or 0
-        if index not in cls._by_device:
-            cls._by_device[index] = Context(index)
-        return cls._by_device[index]
+        key = (index, threading.get_ident())
+        ctx = cls._by_key.get(key)
+        if ctx is None:
+            with cls._lock:
+                ctx = cls._by_key.get(key)
+                if ctx is None:
+                    ctx = cls._by_key[key] = Context(index)
+        return ctx
+
+    @classmethod
+    def total_launches(cls, device=None):
+        index = torch.cuda.current_device() if device is None else (torch.device(device).index or 0)
+        with cls._lock:
+            return sum(c.launch_count() for (i, _), c in cls._by_key.items() if i == index)
 
     @property
     def stream(self):

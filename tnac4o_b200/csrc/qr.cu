@@ -50,7 +50,8 @@ qr_panel_reg_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, doub
 #pragma unroll
     for (int c = 0; c < JB; ++c) row[c] = (have && c < jb) ? A[(int64_t)(j0 + rel) * lda + j0 + c] : 0.0;
     if (tid < JB * JB) Ts[tid] = 0.0;
-    __syncthreads();
+    // every CTA of the cluster must have started before anyone writes into its shared memory
+    cluster.sync();
 
 #pragma unroll
     for (int j = 0; j < JB; ++j) {
@@ -199,7 +200,7 @@ qr_panel_smem_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, dou
         int i = idx / JB, cc = idx % JB;
         P[idx] = (cc < jb) ? A[(int64_t)(j0 + r_begin + i) * lda + j0 + cc] : 0.0;
     }
-    __syncthreads();
+    cluster.sync();      // all CTAs started (required before the first distributed-shared-memory access)
     for (int j = 0; j < jb; ++j) {
         const int buf = j & 1;
         const int owner = j / rows_per;
@@ -385,7 +386,7 @@ int launch_panel(tn_ctx* ctx, cudaStream_t st, double* A, int lda, int m, int j0
             tn_set_error("QR panel of %d rows is too tall for the cluster panel kernels", m - j0);
             return TN_ERR_ARG;
         }
-        TN_CUDA(cudaFuncSetAttribute(qr_panel_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TN_CUDA(cudaFuncSetAttribute(qr_panel_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024));
         qr_panel_smem_kernel<<<CL, PT, smem, st>>>(A, lda, m, j0, jb, Vall, ldv, T);
     }
     TN_LAUNCHED(ctx);

@@ -376,7 +376,8 @@ int tn_rr_level(tn_ctx* ctx, void* stream, const tn_site* site, int nb, int Dl, 
     if (nb == 0) return TN_OK;
     size_t smem = ((size_t)site->nd * Dr * (site->nl + 1) + (size_t)Dr * site->nr) * sizeof(double);
     TN_REQUIRE(smem <= 220 * 1024, "bond dimension too large for rr_level shared memory");
-    TN_CUDA(cudaFuncSetAttribute(rr_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // a fixed maximum: concurrent host threads must not lower the attribute under each other's launches
+    TN_CUDA(cudaFuncSetAttribute(rr_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     int grid = nb < 4 * ctx->sm_count ? nb : 4 * ctx->sm_count;
     rr_level_kernel<<<grid, 256, smem, as_stream(stream)>>>(nb, Dl, Dr, site->nl, site->nd, site->nr, site->nu, A,
                                                             site->Wtr, RRin, up, up_stride, RRout);
@@ -393,7 +394,7 @@ int tn_marginals(tn_ctx* ctx, void* stream, const tn_site* site, int nb, int Dr,
     if (max_bits) TN_CUDA(cudaMemsetAsync(max_bits, 0, sizeof(unsigned long long), st));
     size_t smem = ((size_t)site->nd * Dr + (size_t)Dr * site->nr + (size_t)site->nd * site->nr) * sizeof(double);
     TN_REQUIRE(smem <= 220 * 1024, "bond dimension too large for marginals shared memory");
-    TN_CUDA(cudaFuncSetAttribute(marginals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TN_CUDA(cudaFuncSetAttribute(marginals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     int grid = nb < 8 * ctx->sm_count ? nb : 8 * ctx->sm_count;
     marginals_kernel<<<grid, 256, smem, st>>>(nb, site->nS, site->nl, site->nd, site->nr, site->nu, Dr, site->Wlu,
                                               site->dmap, site->rmap, T1, RR, root, vind, vstride, nx, prob, cand, flag,

@@ -212,7 +212,7 @@ jacobi_cluster_kernel(double* __restrict__ E, int ldw, int a, int ext, int nc, i
         Sl[i] = v;
     }
     if (tid == 0) myrot = 0;
-    __syncthreads();
+    cluster.sync();      // all CTAs started (required before the first distributed-shared-memory access)
     const int nce = nc + (nc & 1), r1 = nce - 1, half = nce / 2;
     const int sub = lane & 7, grp = lane >> 3;                    // 8 lanes per pair, 4 pairs per warp
     int sweep = 0, converged = 0;

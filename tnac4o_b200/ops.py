@@ -124,4 +124,5 @@ def sort_capacity(n):
 
 
 def launch_count(device=None):
-    return Context.get(device).launch_count()
+    """kernels launched so far on `device` by all host threads of this process"""
+    return Context.total_launches(device)

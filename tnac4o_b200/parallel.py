@@ -58,3 +58,34 @@ class UniformStream:
 
     def draw(self):
         return np.random.rand(self.M)[self.lo:self.hi]
+
+
+def run_concurrently(jobs, device=None):
+    """Run independent solver jobs on ONE GPU at the same time: one host thread and one CUDA stream per job.
+
+    The boundary-MPS build of a single instance is a latency-bound chain of small kernels (cluster QR panels and
+    Jacobi rounds occupy 8 of 148 SMs), so independent instances / rotations / beta steps overlap almost for free.
+    ``jobs`` is a list of zero-argument callables; returns their results in order.  Exceptions are re-raised."""
+    import threading
+    dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    results, errors = [None] * len(jobs), [None] * len(jobs)
+
+    def work(i):
+        try:
+            with torch.cuda.device(dev):
+                stream = torch.cuda.Stream(device=dev)
+                with torch.cuda.stream(stream):
+                    results[i] = jobs[i]()
+                    stream.synchronize()
+        except BaseException as e:      # noqa: BLE001  (re-raised in the caller's thread)
+            errors[i] = e
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for e in errors:
+        if e is not None:
+            raise e
+    return results

@@ -404,7 +404,7 @@ class tnac4o:
     def _finish_search(self, ws, t_rho, t0):
         br = ws['cur']
         n = br.n
-        torch.cuda.synchronize(self._dev())
+        torch.cuda.current_stream(self._dev()).synchronize()
         self.stats['seconds_rhoT'] = t_rho
         self.stats['seconds_search'] = time.time() - t0
         self.energy = br.Eng[:n].cpu().numpy()
@@ -425,7 +425,7 @@ class tnac4o:
         self.logger.info('Searching ground state with beta = %.2f', self.beta)
         self.logger.info('Preprocesing ... ')
         self._setup_rhoT(graduate_truncation=graduate_truncation, Dmax=Dmax, tolS=tolS, tolV=tolV, max_sweeps=max_sweeps)
-        torch.cuda.synchronize(dev)
+        torch.cuda.current_stream(dev).synchronize()
         t_rho = time.time() - t0
         self.logger.info('Elapsed: %.2f seconds', t_rho)
         t0 = time.time()
@@ -462,7 +462,7 @@ class tnac4o:
         self.stats = {}
         self.logger.info('Preprocesing ... ')
         self._setup_rhoT(graduate_truncation=graduate_truncation, Dmax=Dmax, tolS=tolS, tolV=tolV, max_sweeps=max_sweeps)
-        torch.cuda.synchronize(dev)
+        torch.cuda.current_stream(dev).synchronize()
         t_rho = time.time() - t0
         t0 = time.time()
         nsites = self.Nx * self.Ny
@@ -494,7 +494,7 @@ class tnac4o:
                                          ptr(nxt.RL)))
                 cur, nxt = nxt, cur
             check(lib.tn_row_shift(c.handle, c.stream, M, cur.vind.stride(0), ptr(cur.vind)))
-        torch.cuda.synchronize(dev)
+        torch.cuda.current_stream(dev).synchronize()
         self.stats['seconds_rhoT'], self.stats['seconds_search'] = t_rho, time.time() - t0
         self.energy = cur.Eng[:M].cpu().numpy()
         self.degeneracy = 0
@@ -522,7 +522,7 @@ class tnac4o:
         self.stats = {}
         self.logger.info('Preprocesing ... ')
         self._setup_rhoT(graduate_truncation=graduate_truncation, Dmax=Dmax, tolS=tolS, tolV=tolV, max_sweeps=max_sweeps)
-        torch.cuda.synchronize(dev)
+        torch.cuda.current_stream(dev).synchronize()
         t_rho = time.time() - t0
         t0 = time.time()
         ws = self._alloc_search(M, int(np.max(self.N)), self._max_bond())

@@ -94,6 +94,24 @@ int tn_mpo_apply(tn_ctx* ctx, void* stream, int conj, int Dl, int dp, int Dr, in
  * Result in *out (device). */
 int tn_diff_norm(tn_ctx* ctx, void* stream, const double* a, const double* b, int n, double* out);
 
+/* ---------------------------------------------------------------- one boundary-MPS row (tnac4o.py:1683-1694) */
+
+/* Native driver of  psi <- compress_mps( MPO . psi )  = MPS.copy + apply_mpo + compress_mps (mps.py:159-200, 353-359)
+ * with the reference's fixed truncation schedule; issues the primitives above back to back on `stream` without a
+ * host interpreter in the loop.  A_in / W are HOST arrays of L device pointers: A_in[n] is the previous row's tensor
+ * (Dl[n], dphys[n], Dr[n]); W[n] the MPO tensor with legs (wl[n], dphys[n], wr[n], du[n]) for conj = 1 (Hconj=True) or
+ * (wl[n], du[n], wr[n], dphys[n]) for conj = 0.  The compressed row stays on the device inside *out. */
+typedef struct tn_row tn_row;
+int tn_row_compress(tn_ctx* ctx, void* stream, int L, const double* const* A_in, const int* Dl, const int* dphys,
+                    const int* Dr, const double* const* W, const int* wl, const int* wr, const int* du, int conj,
+                    double Dmax, double tolS, double tolV, int max_sweeps, int graduate, tn_row** out);
+/* bond dimensions D[0..L] and physical dimensions d[0..L-1] of the compressed row */
+int tn_row_shapes(const tn_row* row, int* D, int* d);
+/* copy the tensors into caller-owned device buffers (sizes from tn_row_shapes); host outputs: overlap with the
+ * uncompressed state (rhoT_overlap), per-bond discarded weights (L + 1), log2 of the accumulated norm */
+int tn_row_fetch(tn_row* row, double* const* A_out, double* h_overlap, double* h_discarded, double* h_log2norm);
+int tn_row_free(tn_row* row);
+
 /* ---------------------------------------------------------------- branch-and-bound (tnac4o/tnac4o.py) */
 
 /* Per-site constant tables, built by the host with the reference's numpy expressions and uploaded once per

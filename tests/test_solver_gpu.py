@@ -244,3 +244,27 @@ def test_config5_gibbs_L2048_reduced():
     assert np.max(np.abs(E - ins.energy)) < 1e-6
     assert len(np.unique(ins.states, axis=0)) > 1900
     assert -3200 < ins.energy.mean() < -2900                               # reference run: <E> = -3038.85 at M = 10^3
+
+
+@pytest.mark.parametrize('L,D', [(128, 8), (512, 16)])
+def test_native_row_driver_equals_python_mps_methods(L, D):
+    """csrc/mps_native.cu issues the same kernel sequence as tnac4o_b200/mps.py (the mirror of the reference's MPS
+    class): the boundary MPS of every row must come out bit-identical"""
+    J = droplet_couplings(L)
+    a = make(J, L=L)
+    b = make(J, L=L)
+    b.native_rows = False
+    a._setup_rhoT(Dmax=D)
+    b._setup_rhoT(Dmax=D)
+    for ny in range(a.Ny + 1):
+        assert a.rhoT[ny].D == b.rhoT[ny].D
+        for x, y in zip(a.rhoT[ny].A, b.rhoT[ny].A):
+            assert torch.equal(x, y)
+        if ny < a.Ny:
+            assert a.rhoT_overlap[ny] == b.rhoT_overlap[ny]
+            assert a.rhoT_discarded[ny] == b.rhoT_discarded[ny]
+    a._setup_rhoB(Dmax=D)
+    b._setup_rhoB(Dmax=D)
+    for ny in range(a.Ny + 1):
+        for x, y in zip(a.rhoB[ny].A, b.rhoB[ny].A):
+            assert torch.equal(x, y)

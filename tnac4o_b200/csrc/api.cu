@@ -53,6 +53,14 @@ int tn_create(int device, tn_ctx** out) {
         tn_set_error("tnac4o_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
         return TN_ERR_ARG;
     }
+    {
+        // temporaries of the native MPS driver come from the stream-ordered allocator: keep freed blocks cached
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     tn_ctx* ctx = new tn_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;

@@ -310,6 +310,52 @@ class MPS:
         return self.variational_compress(phi, tol=tolV, max_sweeps=max_sweeps, verbose=verbose)
 
 
+def apply_mpo_and_compress(psi, M, Hconj=True, Dmax=np.inf, tolS=1e-16, tolV=1e-10, max_sweeps=4, graduate_truncation=True):
+    """``phi = psi.copy(); phi.apply_mpo(M, Hconj); overlap = phi.compress_mps(...)`` (tnac4o.py:1688-1693) as ONE call into
+    the native row driver (csrc/mps_native.cu), which runs the same kernel sequence as the methods above without the
+    interpreter in the loop.  Returns (phi, overlap); phi is left-canonical with ``discarded`` filled in."""
+    import ctypes
+    from ._native import Context, check, lib
+    L = psi.L
+    dev = psi.device
+    c = Context.get(dev)
+    PtrArr, IntArr = ctypes.c_void_p * L, ctypes.c_int * L
+    A = [a.contiguous() for a in psi.A]
+    W = [w.contiguous() for w in M.W]
+    if not all(M.support):
+        raise ValueError('apply_mpo_and_compress needs an MPO tensor on every site')
+    wl = [w.shape[0] for w in W]
+    wr = [w.shape[2] for w in W]
+    du = [w.shape[3] if Hconj else w.shape[1] for w in W]
+    handle = ctypes.c_void_p()
+    dmax = float(min(Dmax, 2.0 ** 40))
+    check(lib.tn_row_compress(c.handle, c.stream, L, PtrArr(*[a.data_ptr() for a in A]), IntArr(*[a.shape[0] for a in A]),
+                              IntArr(*[a.shape[1] for a in A]), IntArr(*[a.shape[2] for a in A]),
+                              PtrArr(*[w.data_ptr() for w in W]), IntArr(*wl), IntArr(*wr), IntArr(*du), int(bool(Hconj)),
+                              dmax, float(tolS), float(tolV), int(max_sweeps), int(bool(graduate_truncation)),
+                              ctypes.byref(handle)))
+    try:
+        D, d = (ctypes.c_int * (L + 1))(), IntArr()
+        check(lib.tn_row_shapes(handle, D, d))
+        phi = MPS.__new__(MPS)
+        phi.device, phi.L, phi.zero, phi.dtype = dev, L, psi.zero, psi.dtype
+        phi.D, phi.d = list(D), list(d)
+        phi.A = [torch.empty((D[n], d[n], D[n + 1]), dtype=F64, device=dev) for n in range(L)]
+        overlap, log2norm = ctypes.c_double(0.0), ctypes.c_double(0.0)
+        disc = (ctypes.c_double * (L + 1))()
+        check(lib.tn_row_fetch(handle, PtrArr(*[a.data_ptr() for a in phi.A]), ctypes.byref(overlap), disc,
+                               ctypes.byref(log2norm)))
+    finally:
+        lib.tn_row_free(handle)
+    phi.C = torch.ones((1, 1), dtype=F64, device=dev)
+    phi.pC = L
+    phi._log2_normC = psi._log2_normC + log2norm.value
+    phi.reset_R()
+    phi.reset_S()
+    phi.discarded = [float(x) for x in disc]
+    return phi, overlap.value
+
+
 class MPO:
     """holder of rank-4 tensors W[n] with legs (left, out, right, in) (mps.py:818-884)"""
 

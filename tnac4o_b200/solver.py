@@ -67,6 +67,7 @@ class tnac4o:
         self.device = None if device is None else torch.device(device)
         self.stats = {}
         self._sites = None
+        self.native_rows = True      # boundary-MPS rows through the native driver (False: Python MPS methods)
         if J is not None:
             self.J = upper_triangular(J, self.L)
             self.J0 = self.J.copy()
@@ -162,10 +163,15 @@ class tnac4o:
         self.rhoT_discarded = [0] * (self.Ny + 1)
         self.rhoT[-1] = mps.MPS(d=1, L=self.Nx, Dmax=1, initial='X', device=dev)
         for ny in range(self.Ny - 1, -1, -1):
-            psi = self.rhoT[ny + 1].copy()
-            psi.apply_mpo(self._row_mpo(ny), Hconj=True)
-            self.rhoT_overlap[ny] = psi.compress_mps(Dmax=Dmax, tolS=tolS, tolV=tolV, max_sweeps=max_sweeps,
-                                                     graduate_truncation=graduate_truncation, verbose=False)
+            if self.native_rows:
+                psi, self.rhoT_overlap[ny] = mps.apply_mpo_and_compress(
+                    self.rhoT[ny + 1], self._row_mpo(ny), Hconj=True, Dmax=Dmax, tolS=tolS, tolV=tolV, max_sweeps=max_sweeps,
+                    graduate_truncation=graduate_truncation)
+            else:       # the same kernel sequence driven from Python through the reference's MPS interface
+                psi = self.rhoT[ny + 1].copy()
+                psi.apply_mpo(self._row_mpo(ny), Hconj=True)
+                self.rhoT_overlap[ny] = psi.compress_mps(Dmax=Dmax, tolS=tolS, tolV=tolV, max_sweeps=max_sweeps,
+                                                         graduate_truncation=graduate_truncation, verbose=False)
             self.rhoT_discarded[ny] = max(psi.discarded)
             self.rhoT[ny] = psi
 
@@ -175,10 +181,14 @@ class tnac4o:
         self.rhoB = [None] * (self.Ny + 1)
         self.rhoB[0] = mps.MPS(d=1, L=self.Nx, Dmax=1, initial='X', device=dev)
         for ny in range(self.Ny):
-            psi = self.rhoB[ny].copy()
-            psi.apply_mpo(self._row_mpo(ny), Hconj=False)
-            psi.compress_mps(Dmax=Dmax, tolS=tolS, tolV=tolV, max_sweeps=max_sweeps,
-                             graduate_truncation=graduate_truncation, verbose=False)
+            if self.native_rows:
+                psi, _ = mps.apply_mpo_and_compress(self.rhoB[ny], self._row_mpo(ny), Hconj=False, Dmax=Dmax, tolS=tolS,
+                                                    tolV=tolV, max_sweeps=max_sweeps, graduate_truncation=graduate_truncation)
+            else:
+                psi = self.rhoB[ny].copy()
+                psi.apply_mpo(self._row_mpo(ny), Hconj=False)
+                psi.compress_mps(Dmax=Dmax, tolS=tolS, tolV=tolV, max_sweeps=max_sweeps,
+                                 graduate_truncation=graduate_truncation, verbose=False)
             self.rhoB[ny + 1] = psi
 
     # ------------------------------------------------------------------ preconditioning

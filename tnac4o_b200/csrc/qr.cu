@@ -27,28 +27,37 @@ constexpr int JB = 16;         // inner panel width
 constexpr int NB = 128;        // outer block width
 
 // ---------------------------------------------------------------------------------------------------------------
-// register-resident panel factorisation: rows_per <= PT
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(PT, 1)
+// register-resident panel factorisation: each of the RT threads of a CTA owns up to RPT rows (RT * RPT >= rows_per)
+constexpr int RT = 256;        // threads per CTA of the register kernel
+constexpr int RPT = 4;         // rows per thread
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(RT, 1)
 qr_panel_reg_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, double* __restrict__ Vall, int ldv,
                     double* __restrict__ Tout) {
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
-    __shared__ double red[PT / 32][JB];
+    __shared__ double red[RT / 32][JB];
     __shared__ double cw[2][CL][JB];          // per-CTA partial dots, double-buffered by column parity
     __shared__ double prow[2][JB];            // pivot row broadcast
     __shared__ double sc[JB];                 // tau * v^T a_c
     __shared__ double par[4];                 // beta, tau, scale
     __shared__ double Ts[JB * JB];
-    __shared__ double gcol[JB];
+    __shared__ double stage[JB];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m_rem = m - j0;
     const int rows_per = (m_rem + CL - 1) / CL;
-    const int rel = rank * rows_per + tid;                      // my row, relative to j0
-    const bool have = (tid < rows_per) && (rel < m_rem);
-    double row[JB];
+    int rel[RPT];
+    bool have[RPT];
+    double row[RPT][JB];
 #pragma unroll
-    for (int c = 0; c < JB; ++c) row[c] = (have && c < jb) ? A[(int64_t)(j0 + rel) * lda + j0 + c] : 0.0;
+    for (int q = 0; q < RPT; ++q) {
+        const int loc = tid + q * RT;
+        rel[q] = rank * rows_per + loc;                          // my row, relative to j0
+        have[q] = (loc < rows_per) && (rel[q] < m_rem);
+#pragma unroll
+        for (int c = 0; c < JB; ++c) row[q][c] = (have[q] && c < jb) ? A[(int64_t)(j0 + rel[q]) * lda + j0 + c] : 0.0;
+    }
     if (tid < JB * JB) Ts[tid] = 0.0;
     // every CTA of the cluster must have started before anyone writes into its shared memory
     cluster.sync();
@@ -58,12 +67,17 @@ qr_panel_reg_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, doub
         if (j >= jb) break;
         const int buf = j & 1;
         const int owner = j / rows_per;
-        // ---- products with the rows strictly below the pivot
+        // ---- products with the rows strictly below the pivot, summed over my rows
         double v[JB];
-        const double x = (have && rel > j) ? row[j] : 0.0;
 #pragma unroll
-        for (int c = 0; c < JB; ++c) v[c] = x * row[c];
-        // transposing butterfly: after the 4 halving steps lane l holds the warp total of value idx(l)
+        for (int c = 0; c < JB; ++c) v[c] = 0.0;
+#pragma unroll
+        for (int q = 0; q < RPT; ++q) {
+            const double x = (have[q] && rel[q] > j) ? row[q][j] : 0.0;
+#pragma unroll
+            for (int c = 0; c < JB; ++c) v[c] += x * row[q][c];
+        }
+        // transposing butterfly: after the halving steps lane l holds the warp total of value idx(l)
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             bool up = lane & 16;
@@ -92,34 +106,33 @@ qr_panel_reg_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, doub
             int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
             red[warp][idx] = v[0];
         }
-        if (have && rel == j) {
 #pragma unroll
-            for (int c = 0; c < JB; ++c) gcol[c] = row[c];       // stage the pivot row (owner CTA only)
+        for (int q = 0; q < RPT; ++q) {
+            if (have[q] && rel[q] == j) {
+#pragma unroll
+                for (int c = 0; c < JB; ++c) stage[c] = row[q][c];     // stage the pivot row (owner CTA only)
+            }
         }
         __syncthreads();
-        if (tid < JB * 32) {
-            int idx = tid >> 5;
-            double s = warp_sum(red[lane][idx]);
-            if (lane < CL) {
-                double* remote = cluster.map_shared_rank(&cw[buf][rank][idx], lane);
-                *remote = s;
-            }
-            if (rank == owner && lane >= 8 && lane < 8 + CL) {
-                double* remote = cluster.map_shared_rank(&prow[buf][idx], lane - 8);
-                *remote = gcol[idx];
+        if (tid < JB) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < RT / 32; ++w) s += red[w][tid];
+#pragma unroll
+            for (int r = 0; r < CL; ++r) *cluster.map_shared_rank(&cw[buf][rank][tid], r) = s;
+            if (rank == owner) {
+                const double pv = stage[tid];
+#pragma unroll
+                for (int r = 0; r < CL; ++r) *cluster.map_shared_rank(&prow[buf][tid], r) = pv;
             }
         }
         cluster.sync();
-        // ---- reflector parameters, tau * v^T a_c for c > j, column j of T
+        // ---- reflector parameters, tau * v^T a_c for c > j and column j of T: 16 lanes, redundant scalar work
         if (tid < JB) {
-            double w = 0.0;
+            double wc = 0.0, wj = 0.0;
 #pragma unroll
-            for (int r = 0; r < CL; ++r) w += cw[buf][r][tid];
-            gcol[tid] = w;                                       // w_c = sum_{i > pivot} x_i a_ic
-        }
-        __syncthreads();
-        if (tid == 0) {
-            const double wj = gcol[j], alpha = prow[buf][j];
+            for (int r = 0; r < CL; ++r) { wc += cw[buf][r][tid]; wj += cw[buf][r][j]; }
+            const double alpha = prow[buf][j];
             double beta, tau, scale;
             if (wj == 0.0) { beta = alpha; tau = 0.0; scale = 0.0; }
             else {
@@ -127,45 +140,47 @@ qr_panel_reg_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, doub
                 tau = (beta - alpha) / beta;
                 scale = 1.0 / (alpha - beta);
             }
-            par[0] = beta; par[1] = tau; par[2] = scale;
-        }
-        __syncthreads();
-        const double beta = par[0], tau = par[1], scale = par[2];
-        if (tid < JB) {
-            // v^T a_c = a_c[pivot] + scale * w_c  (v = e_pivot + scale * x below the pivot)
-            double vta = prow[buf][tid] + scale * gcol[tid];
+            // v^T a_c = a_c[pivot] + scale * w_c  (v = e_pivot + scale * x below the pivot); for c < j this is the
+            // Gram entry (V^T V)[c][j] needed by T[0:j, j] = -tau * T[0:j, 0:j] * (V[:, 0:j]^T v_j)
+            const double vta = prow[buf][tid] + scale * wc;
             sc[tid] = tau * vta;
-            // T[0:j, j] = -tau * T[0:j, 0:j] * (V[:, 0:j]^T v_j); the Gram entries are vta for c < j
-            __syncwarp(0xffff);
-            if (tid < j) {
-                double s = 0.0;
-                for (int k = tid; k < j; ++k) s += Ts[tid * JB + k] * (prow[buf][k] + scale * gcol[k]);
-                Ts[tid * JB + j] = -tau * s;
+            double s = 0.0;
+            for (int k = 0; k < j; ++k) {
+                const double gk = __shfl_sync(0xffffu, vta, k);
+                if (k >= tid) s += Ts[tid * JB + k] * gk;
             }
-            if (tid == j) Ts[j * JB + j] = tau;
+            if (tid < j) Ts[tid * JB + j] = -tau * s;
+            if (tid == j) { Ts[j * JB + j] = tau; par[0] = beta; par[1] = tau; par[2] = scale; }
         }
         __syncthreads();
-        // ---- apply the reflector to my row
-        if (have) {
-            if (rel > j) {
-                const double vi = row[j] * scale;
+        const double beta = par[0], scale = par[2];
+        // ---- apply the reflector to my rows
 #pragma unroll
-                for (int c = 0; c < JB; ++c) if (c > j) row[c] -= vi * sc[c];
-                row[j] = vi;
-            } else if (rel == j) {
+        for (int q = 0; q < RPT; ++q) {
+            if (have[q]) {
+                if (rel[q] > j) {
+                    const double vi = row[q][j] * scale;
 #pragma unroll
-                for (int c = 0; c < JB; ++c) if (c > j) row[c] -= sc[c];
-                row[j] = beta;
+                    for (int c = 0; c < JB; ++c) if (c > j) row[q][c] -= vi * sc[c];
+                    row[q][j] = vi;
+                } else if (rel[q] == j) {
+#pragma unroll
+                    for (int c = 0; c < JB; ++c) if (c > j) row[q][c] -= sc[c];
+                    row[q][j] = beta;
+                }
             }
         }
     }
     // ---- write R (upper triangle of the pivot rows) and the explicit V
-    if (have) {
 #pragma unroll
-        for (int c = 0; c < JB; ++c) {
-            if (c < jb) {
-                if (rel <= c) A[(int64_t)(j0 + rel) * lda + j0 + c] = row[c];
-                Vall[(int64_t)(j0 + rel) * ldv + j0 + c] = (rel > c) ? row[c] : (rel == c ? 1.0 : 0.0);
+    for (int q = 0; q < RPT; ++q) {
+        if (have[q]) {
+#pragma unroll
+            for (int c = 0; c < JB; ++c) {
+                if (c < jb) {
+                    if (rel[q] <= c) A[(int64_t)(j0 + rel[q]) * lda + j0 + c] = row[q][c];
+                    Vall[(int64_t)(j0 + rel[q]) * ldv + j0 + c] = (rel[q] > c) ? row[q][c] : (rel[q] == c ? 1.0 : 0.0);
+                }
             }
         }
     }
@@ -378,8 +393,8 @@ __global__ void qr_finish_kernel(const double* __restrict__ A, int lda, int m, i
 
 int launch_panel(tn_ctx* ctx, cudaStream_t st, double* A, int lda, int m, int j0, int jb, double* Vall, int ldv, double* T) {
     const int rows_per = ceil_div(m - j0, CL);
-    if (rows_per <= PT) {
-        qr_panel_reg_kernel<<<CL, PT, 0, st>>>(A, lda, m, j0, jb, Vall, ldv, T);
+    if (rows_per <= RT * RPT) {
+        qr_panel_reg_kernel<<<CL, RT, 0, st>>>(A, lda, m, j0, jb, Vall, ldv, T);
     } else {
         size_t smem = (size_t)rows_per * JB * sizeof(double);
         if (smem > 150 * 1024) {

@@ -52,6 +52,7 @@ wrap(ops, 'diff_norm', lambda a, k: 'diff_norm')
 
 Nx, Ny = SHAPES[L]
 ins = tnac4o_b200.tnac4o(mode='Ising', Nx=Nx, Ny=Ny, Nc=8, J=droplet_couplings(L), beta=3)
+ins.native_rows = False          # same kernel sequence as the native row driver, but every primitive call is visible here
 ins.search_ground_state(M=M, relative_P_cutoff=1e-8, Dmax=D)       # warm-up (not instrumented meaningfully)
 log.clear()
 torch.cuda.synchronize()

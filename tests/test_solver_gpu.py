@@ -71,6 +71,7 @@ def test_boundary_mps_against_oracle(J128):
     ref = make(J128, cls=RefSolver)
     ref._setup_rhoT(Dmax=8)
     ins = make(J128)
+    ins.build_rhoT0 = True
     ins._setup_rhoT(Dmax=8)
     for ny in range(4):
         a = [t.cpu().numpy() for t in ins.rhoT[ny].A]
@@ -254,6 +255,7 @@ def test_native_row_driver_equals_python_mps_methods(L, D):
     a = make(J, L=L)
     b = make(J, L=L)
     b.native_rows = False
+    a.build_rhoT0 = b.build_rhoT0 = True
     a._setup_rhoT(Dmax=D)
     b._setup_rhoT(Dmax=D)
     for ny in range(a.Ny + 1):

@@ -62,22 +62,25 @@ qr_panel_reg_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, doub
     // every CTA of the cluster must have started before anyone writes into its shared memory
     cluster.sync();
 
-#pragma unroll
-    for (int j = 0; j < JB; ++j) {
-        if (j >= jb) break;
+    // The register file of every thread is ROTATED by one column per step, so the current column is always slot 0,
+    // the columns still to be updated are slots 1 .. 15-j and the finished reflectors are slots 16-j .. 15.  The loop
+    // body is therefore the same code for every column (a fully unrolled version is 160 KB of SASS and runs out of
+    // the instruction cache).
+#pragma unroll 1
+    for (int j = 0; j < jb; ++j) {
         const int buf = j & 1;
         const int owner = j / rows_per;
-        // ---- products with the rows strictly below the pivot, summed over my rows
+        // ---- products of column j with every slot over the rows strictly below the pivot, summed over my rows
         double v[JB];
 #pragma unroll
         for (int c = 0; c < JB; ++c) v[c] = 0.0;
 #pragma unroll
         for (int q = 0; q < RPT; ++q) {
-            const double x = (have[q] && rel[q] > j) ? row[q][j] : 0.0;
+            const double x = (have[q] && rel[q] > j) ? row[q][0] : 0.0;
 #pragma unroll
             for (int c = 0; c < JB; ++c) v[c] += x * row[q][c];
         }
-        // transposing butterfly: after the halving steps lane l holds the warp total of value idx(l)
+        // transposing butterfly: after the halving steps lane l holds the warp total of slot idx(l)
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             bool up = lane & 16;
@@ -127,26 +130,27 @@ qr_panel_reg_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, doub
             }
         }
         cluster.sync();
-        // ---- reflector parameters, tau * v^T a_c for c > j and column j of T: 16 lanes, redundant scalar work
+        // ---- reflector parameters, tau * v^T a_slot and column j of T: 16 lanes, redundant scalar work
         if (tid < JB) {
-            double wc = 0.0, wj = 0.0;
+            double wc = 0.0, w0 = 0.0;
 #pragma unroll
-            for (int r = 0; r < CL; ++r) { wc += cw[buf][r][tid]; wj += cw[buf][r][j]; }
-            const double alpha = prow[buf][j];
+            for (int r = 0; r < CL; ++r) { wc += cw[buf][r][tid]; w0 += cw[buf][r][0]; }
+            const double alpha = prow[buf][0];
             double beta, tau, scale;
-            if (wj == 0.0) { beta = alpha; tau = 0.0; scale = 0.0; }
+            if (w0 == 0.0) { beta = alpha; tau = 0.0; scale = 0.0; }
             else {
-                beta = -copysign(sqrt(alpha * alpha + wj), alpha);
+                beta = -copysign(sqrt(alpha * alpha + w0), alpha);
                 tau = (beta - alpha) / beta;
                 scale = 1.0 / (alpha - beta);
             }
-            // v^T a_c = a_c[pivot] + scale * w_c  (v = e_pivot + scale * x below the pivot); for c < j this is the
-            // Gram entry (V^T V)[c][j] needed by T[0:j, j] = -tau * T[0:j, 0:j] * (V[:, 0:j]^T v_j)
+            // v^T a_slot = a_slot[pivot] + scale * w_slot  (v = e_pivot + scale * x below the pivot); for the finished
+            // reflectors (slots 16-j ..) this is the Gram entry (V^T V)[c][j] needed by
+            // T[0:j, j] = -tau * T[0:j, 0:j] * (V[:, 0:j]^T v_j)
             const double vta = prow[buf][tid] + scale * wc;
             sc[tid] = tau * vta;
             double s = 0.0;
             for (int k = 0; k < j; ++k) {
-                const double gk = __shfl_sync(0xffffu, vta, k);
+                const double gk = __shfl_sync(0xffffu, vta, JB - j + k);      // column k sits in slot 16 - j + k
                 if (k >= tid) s += Ts[tid * JB + k] * gk;
             }
             if (tid < j) Ts[tid * JB + j] = -tau * s;
@@ -154,32 +158,38 @@ qr_panel_reg_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, doub
         }
         __syncthreads();
         const double beta = par[0], scale = par[2];
-        // ---- apply the reflector to my rows
+        const int last = JB - 1 - j;                 // slots 1 .. last are the columns still to be updated
+        // ---- apply the reflector to my rows, then rotate the slots
 #pragma unroll
         for (int q = 0; q < RPT; ++q) {
             if (have[q]) {
                 if (rel[q] > j) {
-                    const double vi = row[q][j] * scale;
+                    const double vi = row[q][0] * scale;
 #pragma unroll
-                    for (int c = 0; c < JB; ++c) if (c > j) row[q][c] -= vi * sc[c];
-                    row[q][j] = vi;
+                    for (int c = 1; c < JB; ++c) if (c <= last) row[q][c] -= vi * sc[c];
+                    row[q][0] = vi;
                 } else if (rel[q] == j) {
 #pragma unroll
-                    for (int c = 0; c < JB; ++c) if (c > j) row[q][c] -= sc[c];
-                    row[q][j] = beta;
+                    for (int c = 1; c < JB; ++c) if (c <= last) row[q][c] -= sc[c];
+                    row[q][0] = beta;
                 }
             }
+            const double t0 = row[q][0];
+#pragma unroll
+            for (int c = 0; c < JB - 1; ++c) row[q][c] = row[q][c + 1];
+            row[q][JB - 1] = t0;
         }
     }
-    // ---- write R (upper triangle of the pivot rows) and the explicit V
+    // ---- write R (upper triangle of the pivot rows) and the explicit V; slot s holds column (s + jb) mod 16
 #pragma unroll
     for (int q = 0; q < RPT; ++q) {
         if (have[q]) {
 #pragma unroll
-            for (int c = 0; c < JB; ++c) {
+            for (int sl = 0; sl < JB; ++sl) {
+                const int c = (sl + jb) & (JB - 1);
                 if (c < jb) {
-                    if (rel[q] <= c) A[(int64_t)(j0 + rel[q]) * lda + j0 + c] = row[q][c];
-                    Vall[(int64_t)(j0 + rel[q]) * ldv + j0 + c] = (rel[q] > c) ? row[q][c] : (rel[q] == c ? 1.0 : 0.0);
+                    if (rel[q] <= c) A[(int64_t)(j0 + rel[q]) * lda + j0 + c] = row[q][sl];
+                    Vall[(int64_t)(j0 + rel[q]) * ldv + j0 + c] = (rel[q] > c) ? row[q][sl] : (rel[q] == c ? 1.0 : 0.0);
                 }
             }
         }

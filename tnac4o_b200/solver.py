@@ -68,6 +68,7 @@ class tnac4o:
         self.stats = {}
         self._sites = None
         self.native_rows = True      # boundary-MPS rows through the native driver (False: Python MPS methods)
+        self.build_rhoT0 = False     # the reference also contracts the last row (rhoT[0] / rhoB[Ny]), which nothing reads
         if J is not None:
             self.J = upper_triangular(J, self.L)
             self.J0 = self.J.copy()
@@ -162,7 +163,9 @@ class tnac4o:
         self.rhoT_overlap = [1] * (self.Ny + 1)
         self.rhoT_discarded = [0] * (self.Ny + 1)
         self.rhoT[-1] = mps.MPS(d=1, L=self.Nx, Dmax=1, initial='X', device=dev)
-        for ny in range(self.Ny - 1, -1, -1):
+        # rhoT[0] (all rows contracted) is never read by the searches or by the preconditioning -- the reference
+        # builds it anyway (tnac4o.py:1683); here it is skipped unless `build_rhoT0` is set
+        for ny in range(self.Ny - 1, -1 if self.build_rhoT0 else 0, -1):
             if self.native_rows:
                 psi, self.rhoT_overlap[ny] = mps.apply_mpo_and_compress(
                     self.rhoT[ny + 1], self._row_mpo(ny), Hconj=True, Dmax=Dmax, tolS=tolS, tolV=tolV, max_sweeps=max_sweeps,
@@ -180,7 +183,8 @@ class tnac4o:
         dev = self._dev()
         self.rhoB = [None] * (self.Ny + 1)
         self.rhoB[0] = mps.MPS(d=1, L=self.Nx, Dmax=1, initial='X', device=dev)
-        for ny in range(self.Ny):
+        # rhoB[Ny] is never read by the preconditioning (tnac4o.py:1838 loops over the interior cuts only)
+        for ny in range(self.Ny if self.build_rhoT0 else self.Ny - 1):
             if self.native_rows:
                 psi, _ = mps.apply_mpo_and_compress(self.rhoB[ny], self._row_mpo(ny), Hconj=False, Dmax=Dmax, tolS=tolS,
                                                     tolV=tolV, max_sweeps=max_sweeps, graduate_truncation=graduate_truncation)
@@ -409,7 +413,7 @@ class tnac4o:
         return groups
 
     def _max_bond(self):
-        return max(max(psi.D) for psi in self.rhoT)
+        return max(max(psi.D) for psi in self.rhoT if psi is not None)
 
     def _finish_search(self, ws, t_rho, t0):
         br = ws['cur']

@@ -66,6 +66,8 @@ def o_var(self, phi, tol=None, max_sweeps=1):
 gmps.MPS.variational_compress = g_var
 omps.RefMPS.variational_compress = o_var
 ins = tnac4o_b200.tnac4o(mode='Ising', Nx=Nx, Ny=Ny, Nc=8, J=J, beta=3)
+ins.build_rhoT0 = True
+ins.native_rows = False
 ref = RefSolver(mode='Ising', Nx=Nx, Ny=Ny, Nc=8, J=J, beta=3)
 ins._setup_rhoT(Dmax=D)
 ref._setup_rhoT(Dmax=D)

@@ -219,8 +219,7 @@ def run_gpu(args):
         step(True)
     barrier()
     total_e2e = time.perf_counter() - t_begin
-    h2d = B * sum(t.numel() * t.element_size() for row in ins._sites for s in row
-                  for t in (s.Wlu, s.WtrU, s.Wmpo, s.dmap, s.rmap, s.Es, s.Esl, s.Esu))
+    h2d = B * sum(s.h2d_bytes for row in ins._sites for s in row)
     d2h = B * (ins.energy.nbytes + ins.states.nbytes + ins.probability.nbytes + 3 * 8)
     # single-instance latency (one stream), two extra steps outside the timed region
     lat_runs = [step(False, [ins]) for _ in range(2)]

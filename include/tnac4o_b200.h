@@ -128,6 +128,13 @@ typedef struct tn_site {
     const double* Esu;    /* [nS][nu]  coupling upwards      (tnac4o.py:1529) */
 } tn_site;
 
+/* Builds the per-site tables on the device from the exponent tables E0[s] = beta (min Es - Es[s]), E1[s][l], E4[s][u]
+ * (tnac4o.py:1571-1583), the gauge vectors Xu/Xl/Xr/Xd and the bond maps -- the compact form of _peps_tensor
+ * (tnac4o.py:1586-1607) and of its trace over the cell state (tnac4o.py:1686).  Wmpo has the MPO leg order (l, d, r, u). */
+int tn_build_site_tables(tn_ctx* ctx, void* stream, int nS, int nl, int nd, int nr, int nu, const double* E0,
+                         const double* E1, const double* E4, const double* Xu, const double* Xl, const double* Xr,
+                         const double* Xd, const uint8_t* dmap, const uint8_t* rmap, double* Wlu, double* WtrU, double* Wmpo);
+
 /* Right environments of one row level for nb row-start branches (tnac4o.py:1776-1782):
  *   RRout[b][a][l] = sum_{p,b',r} A[a,p,b'] RRin[b][b'][r] Wtr[l,p,r,u_b] / nfactor,  u_b = up[b * up_stride].
  * A (Dl, nd, Dr); RRin (nb, Dr, nr); RRout (nb, Dl, nl). */

@@ -185,3 +185,20 @@ def test_energy_ising_kernel(J128):
     states = np.random.default_rng(0).integers(0, 2, size=(300, 128)).astype(np.int8)
     E = tnac4o_b200.energy_Jij(J128, states)
     assert np.max(np.abs(E - energy_ising_dense(J128, states))) < 1e-10
+
+
+def test_device_built_site_tables_match_host_expressions(J128):
+    """tn_build_site_tables against the host restatement of _peps_tensor (tnac4o_b200/model.py: boltzmann, traced)"""
+    from tnac4o_b200.model import IsingLattice, SiteTables, upper_triangular
+    lat = IsingLattice(upper_triangular(J128, 128), 4, 4, 8)
+    rng = np.random.default_rng(0)
+    X = tuple(np.exp(rng.uniform(-1, 1, size=(4, 4, 16))) for _ in range(4))          # non-trivial gauges
+    for ny, nx in [(0, 0), (1, 2), (3, 3), (2, 0)]:
+        t = SiteTables(lat, ny, nx, 3.0, X, dev())
+        Xu, Xl, Xr, Xd = X
+        Wc, dmap, rmap = lat.boltzmann(ny, nx, 3.0, Xu[ny][nx], Xl[ny][nx], Xr[ny][nx], Xd[ny][nx])
+        Wtr = lat.traced(Wc, dmap, rmap, t.nd, t.nr)
+        scale = np.max(Wc)
+        assert np.max(np.abs(t.Wlu.cpu().numpy() - Wc.transpose(1, 2, 0))) <= 1e-15 * scale
+        assert np.max(np.abs(t.Wmpo.cpu().numpy() - Wtr)) <= 4e-15 * np.max(Wtr)
+        assert np.max(np.abs(t.WtrU.cpu().numpy() - Wtr.transpose(3, 0, 1, 2))) <= 4e-15 * np.max(Wtr)

@@ -48,6 +48,7 @@ _SIGS = {
     'tn_row_shapes': (c_int, [P, P, P]),
     'tn_row_fetch': (c_int, [P, P, POINTER(c_double), P, POINTER(c_double)]),
     'tn_row_free': (c_int, [P]),
+    'tn_build_site_tables': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P, P]),
     'tn_rr_level': (c_int, [P, P, POINTER(TnSite), c_int, c_int, c_int, P, P, P, c_int, P]),
     'tn_marginals': (c_int, [P, P, POINTER(TnSite), c_int, c_int, P, P, P, P, c_int, c_int, P, P, P, P, P]),
     'tn_select': (c_int, [P, P, P, c_int64, P, c_double, P, P, P, POINTER(c_int)]),

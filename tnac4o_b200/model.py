@@ -109,6 +109,20 @@ class IsingLattice:
         Wc = Wc * Xd[dmap][:, None, None]
         return Wc, dmap, rmap
 
+    def exponents(self, ny, nx, beta):
+        """beta-scaled, shifted energies E0[s], E1[s, l], E4[s, u] whose sum is exponentiated (tnac4o.py:1571-1583) and
+        the bond maps; the small host-side input of the device table builder"""
+        n = self.sN[ny][nx]
+        st = cell_spins(n)
+        Jin = self.Jin[ny][nx]
+        Es = np.sum(np.dot(st, np.triu(Jin, 1)) * st, 1) + np.dot(st, Jin.diagonal())
+        E0 = beta * (np.min(Es) - Es)
+        E1 = np.dot(np.dot(st, self.Jl[ny][nx]), cell_spins(self.sl[ny][nx]).T)
+        E1 = beta * (np.min(E1) - E1)
+        E4 = np.dot(np.dot(st, self.Ju[ny][nx]), cell_spins(self.su[ny][nx]).T)
+        E4 = beta * (np.min(E4) - E4)
+        return E0, E1, E4, pext_table(n, self.id[ny][nx]), pext_table(n, self.ir[ny][nx])
+
     @staticmethod
     def traced(Wc, dmap, rmap, nd, nr):
         """sum over the cell state: legs (l, d, r, u); terms added in ascending s like np.sum(axis=0) (tnac4o.py:1686)"""
@@ -119,24 +133,35 @@ class IsingLattice:
 
 
 class SiteTables:
-    """Device copies of one site's constants plus the `tn_site` descriptor handed to the kernels."""
+    """Device copies of one site's constants plus the `tn_site` descriptor handed to the kernels.  Only the small
+    exponent / energy tables cross PCIe (~130 KiB per chimera site); the 1.5 MiB of Boltzmann-weight tables are
+    built on the device (tn_build_site_tables)."""
 
     def __init__(self, lattice, ny, nx, beta, X, device):
+        from ._native import Context, check, lib
         Xu, Xl, Xr, Xd = X
-        Wc, dmap, rmap = lattice.boltzmann(ny, nx, beta, Xu[ny][nx], Xl[ny][nx], Xr[ny][nx], Xd[ny][nx])
-        self.nS = Wc.shape[0]
-        self.nl, self.nu = Wc.shape[1], Wc.shape[2]
+        E0, E1, E4, dmap, rmap = lattice.exponents(ny, nx, beta)
+        self.nS = E0.shape[0]
+        self.nl, self.nu = E1.shape[1], E4.shape[1]
         self.nd, self.nr = int(2 ** lattice.sd[ny][nx]), int(2 ** lattice.sr[ny][nx])
-        Wtr = lattice.traced(Wc, dmap, rmap, self.nd, self.nr)                       # (l, d, r, u)
         Es, Esl, Esu = lattice.energy_tables(ny, nx)
         self.host_dmap, self.host_rmap = dmap, rmap
         dev = lambda a, dt=np.float64: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(device)
-        self.Wlu = dev(Wc.transpose(1, 2, 0))                                         # [l][u][s]
-        self.WtrU = dev(Wtr.transpose(3, 0, 1, 2))                                    # [u][l][d][r]
-        self.Wmpo = dev(Wtr)                                                          # (l, d, r, u) for the MPO
+        f64 = lambda *shape: torch.empty(shape, dtype=torch.float64, device=device)
         self.dmap = dev(dmap, np.uint8)
         self.rmap = dev(rmap, np.uint8)
         self.Es, self.Esl, self.Esu = dev(Es), dev(Esl.reshape(self.nS, self.nl)), dev(Esu.reshape(self.nS, self.nu))
+        self.Wlu = f64(self.nl, self.nu, self.nS)                                    # [l][u][s]
+        self.WtrU = f64(self.nu, self.nl, self.nd, self.nr)                          # [u][l][d][r]
+        self.Wmpo = f64(self.nl, self.nd, self.nr, self.nu)                          # (l, d, r, u) for the MPO
+        small = [dev(E0), dev(E1.reshape(self.nS, self.nl)), dev(E4.reshape(self.nS, self.nu)), dev(Xu[ny][nx][:self.nu]),
+                 dev(Xl[ny][nx][:self.nl]), dev(Xr[ny][nx][:self.nr]), dev(Xd[ny][nx][:self.nd])]
+        c = Context.get(device)
+        check(lib.tn_build_site_tables(c.handle, c.stream, self.nS, self.nl, self.nd, self.nr, self.nu,
+                                       *[t.data_ptr() for t in small], self.dmap.data_ptr(), self.rmap.data_ptr(),
+                                       self.Wlu.data_ptr(), self.WtrU.data_ptr(), self.Wmpo.data_ptr()))
+        self._keep = small           # alive until the builder kernels have run (same stream as every later use)
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in small + [self.dmap, self.rmap, self.Es, self.Esl, self.Esu])
         self.c = TnSite(self.nS, self.nl, self.nd, self.nr, self.nu, self.Wlu.data_ptr(), self.WtrU.data_ptr(),
                         self.dmap.data_ptr(), self.rmap.data_ptr(), self.Es.data_ptr(), self.Esl.data_ptr(),
                         self.Esu.data_ptr())

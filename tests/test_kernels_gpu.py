@@ -189,12 +189,13 @@ def test_energy_ising_kernel(J128):
 
 def test_device_built_site_tables_match_host_expressions(J128):
     """tn_build_site_tables against the host restatement of _peps_tensor (tnac4o_b200/model.py: boltzmann, traced)"""
-    from tnac4o_b200.model import IsingLattice, SiteTables, upper_triangular
+    from tnac4o_b200.model import HostTables, IsingLattice, upload_site_tables, upper_triangular
     lat = IsingLattice(upper_triangular(J128, 128), 4, 4, 8)
     rng = np.random.default_rng(0)
     X = tuple(np.exp(rng.uniform(-1, 1, size=(4, 4, 16))) for _ in range(4))          # non-trivial gauges
+    sites, _keep = upload_site_tables(HostTables(lat, 3.0, X), 4, 4, dev())
     for ny, nx in [(0, 0), (1, 2), (3, 3), (2, 0)]:
-        t = SiteTables(lat, ny, nx, 3.0, X, dev())
+        t = sites[ny][nx]
         Xu, Xl, Xr, Xd = X
         Wc, dmap, rmap = lat.boltzmann(ny, nx, 3.0, Xu[ny][nx], Xl[ny][nx], Xr[ny][nx], Xd[ny][nx])
         Wtr = lat.traced(Wc, dmap, rmap, t.nd, t.nr)

@@ -132,40 +132,75 @@ class IsingLattice:
         return W
 
 
-class SiteTables:
-    """Device copies of one site's constants plus the `tn_site` descriptor handed to the kernels.  Only the small
-    exponent / energy tables cross PCIe (~130 KiB per chimera site); the 1.5 MiB of Boltzmann-weight tables are
-    built on the device (tn_build_site_tables)."""
+class HostTables:
+    """Host half of the per-site constants: every small table of every site packed into ONE pinned float64 buffer and
+    one uint8 buffer, so that the upload is two copies per instance (~34 MB at L = 2048)."""
 
-    def __init__(self, lattice, ny, nx, beta, X, device):
-        from ._native import Context, check, lib
+    FIELDS = ('E0', 'E1', 'E4', 'Xu', 'Xl', 'Xr', 'Xd', 'Es', 'Esl', 'Esu')
+
+    def __init__(self, lattice, beta, X):
         Xu, Xl, Xr, Xd = X
-        E0, E1, E4, dmap, rmap = lattice.exponents(ny, nx, beta)
-        self.nS = E0.shape[0]
-        self.nl, self.nu = E1.shape[1], E4.shape[1]
-        self.nd, self.nr = int(2 ** lattice.sd[ny][nx]), int(2 ** lattice.sr[ny][nx])
-        Es, Esl, Esu = lattice.energy_tables(ny, nx)
-        self.host_dmap, self.host_rmap = dmap, rmap
-        dev = lambda a, dt=np.float64: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(device)
+        self.sites, chunks, maps = [], [], []
+        off, moff = 0, 0
+        for ny in range(lattice.Ny):
+            for nx in range(lattice.Nx):
+                E0, E1, E4, dmap, rmap = lattice.exponents(ny, nx, beta)
+                Es, Esl, Esu = lattice.energy_tables(ny, nx)
+                nS, nl, nu = E0.shape[0], E1.shape[1], E4.shape[1]
+                nd, nr = int(2 ** lattice.sd[ny][nx]), int(2 ** lattice.sr[ny][nx])
+                parts = (E0, E1.reshape(nS, nl), E4.reshape(nS, nu), Xu[ny][nx][:nu], Xl[ny][nx][:nl], Xr[ny][nx][:nr],
+                         Xd[ny][nx][:nd], Es, Esl.reshape(nS, nl), Esu.reshape(nS, nu))
+                meta = {'dims': (nS, nl, nd, nr, nu), 'off': {}, 'moff': moff}
+                for name, a in zip(self.FIELDS, parts):
+                    a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+                    meta['off'][name] = (off, a.size)
+                    chunks.append(a)
+                    off += a.size
+                maps.append(np.ascontiguousarray(dmap, dtype=np.uint8))
+                maps.append(np.ascontiguousarray(rmap, dtype=np.uint8))
+                moff += 2 * nS
+                self.sites.append(meta)
+        pin = torch.cuda.is_available()
+        self.f64 = torch.from_numpy(np.concatenate(chunks))
+        self.u8 = torch.from_numpy(np.concatenate(maps))
+        if pin:
+            self.f64, self.u8 = self.f64.pin_memory(), self.u8.pin_memory()
+        self.nbytes = self.f64.numel() * 8 + self.u8.numel()
+
+
+class SiteTables:
+    """Device half: views into the uploaded buffers plus the Boltzmann-weight tables built on the device
+    (tn_build_site_tables), and the `tn_site` descriptor handed to the kernels."""
+
+    def __init__(self, meta, dbuf, dmaps, device):
+        from ._native import Context, check, lib
+        self.nS, self.nl, self.nd, self.nr, self.nu = meta['dims']
+        view = lambda name: dbuf[meta['off'][name][0]:meta['off'][name][0] + meta['off'][name][1]]
+        self.dmap = dmaps[meta['moff']:meta['moff'] + self.nS]
+        self.rmap = dmaps[meta['moff'] + self.nS:meta['moff'] + 2 * self.nS]
+        self.Es, self.Esl, self.Esu = view('Es'), view('Esl'), view('Esu')
         f64 = lambda *shape: torch.empty(shape, dtype=torch.float64, device=device)
-        self.dmap = dev(dmap, np.uint8)
-        self.rmap = dev(rmap, np.uint8)
-        self.Es, self.Esl, self.Esu = dev(Es), dev(Esl.reshape(self.nS, self.nl)), dev(Esu.reshape(self.nS, self.nu))
         self.Wlu = f64(self.nl, self.nu, self.nS)                                    # [l][u][s]
         self.WtrU = f64(self.nu, self.nl, self.nd, self.nr)                          # [u][l][d][r]
         self.Wmpo = f64(self.nl, self.nd, self.nr, self.nu)                          # (l, d, r, u) for the MPO
-        small = [dev(E0), dev(E1.reshape(self.nS, self.nl)), dev(E4.reshape(self.nS, self.nu)), dev(Xu[ny][nx][:self.nu]),
-                 dev(Xl[ny][nx][:self.nl]), dev(Xr[ny][nx][:self.nr]), dev(Xd[ny][nx][:self.nd])]
         c = Context.get(device)
         check(lib.tn_build_site_tables(c.handle, c.stream, self.nS, self.nl, self.nd, self.nr, self.nu,
-                                       *[t.data_ptr() for t in small], self.dmap.data_ptr(), self.rmap.data_ptr(),
+                                       *[view(n).data_ptr() for n in ('E0', 'E1', 'E4', 'Xu', 'Xl', 'Xr', 'Xd')],
+                                       self.dmap.data_ptr(), self.rmap.data_ptr(),
                                        self.Wlu.data_ptr(), self.WtrU.data_ptr(), self.Wmpo.data_ptr()))
-        self._keep = small           # alive until the builder kernels have run (same stream as every later use)
-        self.h2d_bytes = sum(t.numel() * t.element_size() for t in small + [self.dmap, self.rmap, self.Es, self.Esl, self.Esu])
         self.c = TnSite(self.nS, self.nl, self.nd, self.nr, self.nu, self.Wlu.data_ptr(), self.WtrU.data_ptr(),
                         self.dmap.data_ptr(), self.rmap.data_ptr(), self.Es.data_ptr(), self.Esl.data_ptr(),
                         self.Esu.data_ptr())
         self.ref = ctypes.byref(self.c)
+
+
+def upload_site_tables(host, Ny, Nx, device):
+    """two host-to-device copies (pinned, asynchronous on the current stream), then the device table builder per site"""
+    dbuf = host.f64.to(device, non_blocking=True)
+    dmaps = host.u8.to(device, non_blocking=True)
+    flat = [SiteTables(meta, dbuf, dmaps, device) for meta in host.sites]
+    sites = [[flat[ny * Nx + nx] for nx in range(Nx)] for ny in range(Ny)]
+    return sites, (dbuf, dmaps)
 
 
 def upper_triangular(J, L):

@@ -17,7 +17,7 @@ import torch
 
 from . import mps, ops
 from ._native import Context, check, lib, ptr
-from .model import IsingLattice, SiteTables, cell_bits, upper_triangular
+from .model import HostTables, IsingLattice, cell_bits, upload_site_tables, upper_triangular
 
 F64 = torch.float64
 _NEG_INF_BITS = 0x000FFFFFFFFFFFFF          # order-preserving encoding of -inf (common.cuh: ordered_bits)
@@ -67,6 +67,7 @@ class tnac4o:
         self.device = None if device is None else torch.device(device)
         self.stats = {}
         self._sites = None
+        self._host = None
         self.native_rows = True      # boundary-MPS rows through the native driver (False: Python MPS methods)
         self.build_rhoT0 = False     # the reference also contracts the last row (rhoT[0] / rhoB[Ny]), which nothing reads
         if J is not None:
@@ -93,6 +94,7 @@ class tnac4o:
         self.Xr = np.ones((Ny, Nx, np.max(self.lr)))
         self.overlaps_ud = np.empty(shape=[0, Ny - 1])
         self._sites = None
+        self._host = None
 
     def rotate_graph(self, rot=1):
         """quarter turns of the lattice, cumulative (tnac4o.py:290-340)"""
@@ -136,17 +138,30 @@ class tnac4o:
             self.device = torch.device('cuda', torch.cuda.current_device())
         return self.device
 
+    def _host_tables(self):
+        """small per-site tables on the host (pinned), rebuilt when beta or the gauges change"""
+        if self._host is None or self._host_beta != self.beta:
+            self._host = HostTables(self.lat, self.beta, (self.Xu, self.Xl, self.Xr, self.Xd))
+            self._host_beta = self.beta
+            self._sites = None
+        return self._host
+
     def _upload_sites(self):
         dev = self._dev()
-        X = (self.Xu, self.Xl, self.Xr, self.Xd)
-        self._sites = [[SiteTables(self.lat, ny, nx, self.beta, X, dev) for nx in range(self.Nx)] for ny in range(self.Ny)]
+        host = self._host_tables()
+        self._sites, self._site_buffers = upload_site_tables(host, self.Ny, self.Nx, dev)
         self._sites_beta = self.beta
+        self.stats['h2d_bytes'] = host.nbytes
         return self._sites
 
     def _site_tables(self):
         if self._sites is None or self._sites_beta != self.beta:
             self._upload_sites()
         return self._sites
+
+    def drop_device_tables(self):
+        """forget the device copies of the site tables (the next call uploads the host tables again)"""
+        self._sites = None
 
     # ------------------------------------------------------------------ boundary MPS
     def _row_mpo(self, ny):
@@ -215,6 +230,7 @@ class tnac4o:
             self.logger.info('Elapsed: %.2f seconds', time.time() - keep_time)
         self.beta = main_beta
         self._sites = None
+        self._host = None
 
     def _update_conditioning(self, direction='ud', graduate_truncation=False, Dmax=8, tolS=1e-16, tolV=1e-10,
                              max_sweeps=4, max_scale=1024):
@@ -224,6 +240,7 @@ class tnac4o:
             raise NotImplementedError("only direction='ud' is reachable in the reference (tnac4o.py:374-377)")
         cap = 2.0 ** np.floor(np.log2(np.sqrt(max_scale)))
         self._sites = None
+        self._host = None
         self._setup_rhoT(graduate_truncation, Dmax, tolS, tolV, max_sweeps)
         self._setup_rhoB(graduate_truncation, Dmax, tolS, tolV, max_sweeps)
         Nx = self.Nx
@@ -277,6 +294,7 @@ class tnac4o:
         self.overlaps_ud = np.vstack([self.overlaps_ud, overlaps])
         self.rhoB = []
         self._sites = None
+        self._host = None
 
     # ------------------------------------------------------------------ search machinery
     def _key_offsets(self, ny, nx):

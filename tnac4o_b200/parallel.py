@@ -60,32 +60,68 @@ class UniformStream:
         return np.random.rand(self.M)[self.lo:self.hi]
 
 
-def run_concurrently(jobs, device=None):
-    """Run independent solver jobs on ONE GPU at the same time: one host thread and one CUDA stream per job.
+class StreamPool:
+    """Persistent worker threads, each bound to its own CUDA stream (and therefore to its own library context and its
+    own allocator pool): independent solver jobs submitted to the pool overlap on one GPU.
 
     The boundary-MPS build of a single instance is a latency-bound chain of small kernels (cluster QR panels and
-    Jacobi rounds occupy 8 of 148 SMs), so independent instances / rotations / beta steps overlap almost for free.
-    ``jobs`` is a list of zero-argument callables; returns their results in order.  Exceptions are re-raised."""
-    import threading
+    Jacobi rounds occupy 8 of 148 SMs), so independent instances / rotations / beta steps overlap almost for free."""
+
+    def __init__(self, workers, device=None):
+        import queue
+        import threading
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.workers = workers
+        self._q = queue.Queue()
+        self._threads = [threading.Thread(target=self._loop, daemon=True) for _ in range(workers)]
+        for t in self._threads:
+            t.start()
+
+    def _loop(self):
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.Stream(device=self.device)
+            with torch.cuda.stream(stream):
+                while True:
+                    item = self._q.get()
+                    if item is None:
+                        return
+                    job, slot, results, errors, done = item
+                    try:
+                        results[slot] = job()
+                        stream.synchronize()
+                    except BaseException as e:      # noqa: BLE001  (re-raised by run() in the caller's thread)
+                        errors[slot] = e
+                    done.release()
+
+    def run(self, jobs):
+        """run zero-argument callables concurrently; returns their results in order, re-raises the first exception"""
+        import threading
+        results, errors = [None] * len(jobs), [None] * len(jobs)
+        done = threading.Semaphore(0)
+        for i, job in enumerate(jobs):
+            self._q.put((job, i, results, errors, done))
+        for _ in jobs:
+            done.acquire()
+        for e in errors:
+            if e is not None:
+                raise e
+        return results
+
+    def close(self):
+        for _ in self._threads:
+            self._q.put(None)
+        for t in self._threads:
+            t.join()
+
+
+_POOLS = {}
+
+
+def run_concurrently(jobs, device=None):
+    """Run independent solver jobs on ONE GPU at the same time through a cached :class:`StreamPool` with one worker
+    per job.  ``jobs`` is a list of zero-argument callables; returns their results in order."""
     dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
-    results, errors = [None] * len(jobs), [None] * len(jobs)
-
-    def work(i):
-        try:
-            with torch.cuda.device(dev):
-                stream = torch.cuda.Stream(device=dev)
-                with torch.cuda.stream(stream):
-                    results[i] = jobs[i]()
-                    stream.synchronize()
-        except BaseException as e:      # noqa: BLE001  (re-raised in the caller's thread)
-            errors[i] = e
-
-    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
-    for e in errors:
-        if e is not None:
-            raise e
-    return results
+    key = (dev.index, len(jobs))
+    if key not in _POOLS:
+        _POOLS[key] = StreamPool(len(jobs), dev)
+    return _POOLS[key].run(jobs)

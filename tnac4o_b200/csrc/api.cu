@@ -20,6 +20,11 @@ int tn_cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 
 void* tn_scratch(tn_ctx* ctx, int slot, size_t bytes) {
     if (bytes <= ctx->scratch_bytes[slot]) return ctx->scratch[slot];
+    if (ctx->capturing) {
+        tn_set_error("scratch slot %d would have to grow (%zu bytes) during a stream capture", slot, bytes);
+        return nullptr;
+    }
+    ctx->scratch_gen++;
     // grow-only; a grow synchronises the device so that no in-flight kernel still reads the old block
     size_t want = bytes + bytes / 4 + (1 << 20);
     cudaDeviceSynchronize();

@@ -10,16 +10,18 @@
 struct tn_ctx {
     int device = 0;
     int sm_count = 148;
-    static constexpr int SLOTS = 6;   // independent grow-only device scratch areas
-    void* scratch[SLOTS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t scratch_bytes[SLOTS] = {0, 0, 0, 0, 0, 0};
+    static constexpr int SLOTS = 7;   // independent grow-only device scratch areas
+    void* scratch[SLOTS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_bytes[SLOTS] = {0, 0, 0, 0, 0, 0, 0};
+    uint64_t scratch_gen = 0;         // bumped whenever a slot is reallocated (captured graphs hold slot pointers)
+    bool capturing = false;           // a stream capture is in progress: slots must not be reallocated
     void* pinned = nullptr;           // small pinned host buffer for scalar read-backs
     int64_t launches = 0;
 };
 
 void tn_set_error(const char* fmt, ...);
 int tn_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
-enum { TN_SLOT_GEMM = 0, TN_SLOT_QR = 1, TN_SLOT_SVD = 2, TN_SLOT_SEARCH = 3, TN_SLOT_SORT = 4, TN_SLOT_MISC = 5 };
+enum { TN_SLOT_GEMM = 0, TN_SLOT_QR = 1, TN_SLOT_SVD = 2, TN_SLOT_SEARCH = 3, TN_SLOT_SORT = 4, TN_SLOT_MISC = 5, TN_SLOT_STAGE = 6 };
 void* tn_scratch(tn_ctx* ctx, int slot, size_t bytes);   // returns nullptr (and sets the error) on failure
 
 #define TN_CUDA(call)                                                          \

@@ -196,6 +196,17 @@ int tn_sample(tn_ctx* ctx, void* stream, const tn_site* site, int B, int nx, int
               const double* uniforms, const uint8_t* vind, int vstride, const double* Eng, int32_t* parent, int32_t* cell,
               double* Enew);
 
+/* Native driver of the whole branch-and-bound of search_ground_state (tnac4o.py:417-551): the calls above in the
+ * reference's order, row by row and site by site, without a host interpreter in the loop.  HOST inputs: sites
+ * (Ny * Nx descriptors, row-major), A ((Ny + 1) * Nx device pointers, A[ny * Nx + nx] = rhoT[ny].A[nx]; row 0 unused),
+ * D ((Ny + 1) * (Nx + 1) bond dimensions), key_offsets (Ny * Nx * (Nx + 1) bit offsets of the merge key).  DEVICE
+ * outputs sized for M branches; host outputs: number of final branches, largest discarded log2 P, smallest
+ * negativity flag, number of branch marginals evaluated.  Synchronises the stream. */
+int tn_search_ground_state(tn_ctx* ctx, void* stream, int Nx, int Ny, const tn_site* sites, const double* const* A,
+                           const int* D, const uint8_t* key_offsets, int M, double relative_P_cutoff, double min_dEng,
+                           uint8_t* states_out, double* Eng_out, double* prob_out, long long* deg_out, int* h_count,
+                           double* h_pd_max, double* h_neg_min, long long* h_marginals);
+
 /* ascending sort of n (hi, lo, tie) keys; arrays need tn_sort_capacity_for(n) elements */
 int tn_sort_keys(tn_ctx* ctx, void* stream, unsigned long long* hi, unsigned long long* lo, unsigned long long* tie, int n);
 int tn_sort_capacity_for(int n);

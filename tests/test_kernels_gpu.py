@@ -203,3 +203,18 @@ def test_device_built_site_tables_match_host_expressions(J128):
         assert np.max(np.abs(t.Wlu.cpu().numpy() - Wc.transpose(1, 2, 0))) <= 1e-15 * scale
         assert np.max(np.abs(t.Wmpo.cpu().numpy() - Wtr)) <= 4e-15 * np.max(Wtr)
         assert np.max(np.abs(t.WtrU.cpu().numpy() - Wtr.transpose(3, 0, 1, 2))) <= 4e-15 * np.max(Wtr)
+
+
+def test_qr_graph_replay_on_side_stream():
+    """on a non-default stream tn_qr_pos replays a captured CUDA graph per shape: same results as the plain launches"""
+    from tnac4o_b200 import ops
+    rng = np.random.default_rng(11)
+    A = rng.standard_normal((600, 96))
+    Q0, R0, b0 = ops.qr_pos(up(A).clone())                  # default stream: plain launch sequence
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for _ in range(3):                                   # capture, then two replays
+            Q1, R1, b1 = ops.qr_pos(up(A).clone())
+        s.synchronize()
+    assert torch.equal(Q0, Q1) and torch.equal(R0, R1) and int(b0.item()) == int(b1.item())
+    _check_qr(A)

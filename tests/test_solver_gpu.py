@@ -41,6 +41,7 @@ def test_search_phase_with_oracle_environments(J128, M, cut):
     ref.trace = lambda kind, **kw: trace.setdefault((kind, kw['ny'], kw['nx']), kw)
     ref.search_ground_state(M=M, relative_P_cutoff=cut, Dmax=8)
     ins = make(J128)
+    ins.native_search = False          # the spy below hooks the Python site loop
     dev = ins._dev()
     ins._setup_rhoT = lambda **kw: setattr(ins, 'rhoT', [upload_mps(p, dev) for p in ref.rhoT])
     seen = {}
@@ -109,6 +110,7 @@ def test_marginals_end_to_end_against_reference_trace(J128):
     ref.trace = lambda kind, **kw: trace.setdefault((kind, kw['ny'], kw['nx']), kw)
     ref.search_ground_state(M=256, relative_P_cutoff=1e-8, Dmax=8)
     ins = make(J128)
+    ins.native_search = False          # the spy below hooks the Python site loop
     seen = {}
     orig = ins._site_marginals
 
@@ -270,3 +272,16 @@ def test_native_row_driver_equals_python_mps_methods(L, D):
     for ny in range(a.Ny + 1):
         for x, y in zip(a.rhoB[ny].A, b.rhoB[ny].A):
             assert torch.equal(x, y)
+
+
+def test_native_search_driver_equals_python_loop(J128):
+    """csrc/search_native.cu against the Python row / site loop: identical kernels in identical order -> identical results"""
+    for M, cut in ((64, 1e-8), (1024, 0.0)):
+        a, b = make(J128), make(J128)
+        b.native_search = False
+        a.search_ground_state(M=M, relative_P_cutoff=cut, Dmax=8)
+        b.search_ground_state(M=M, relative_P_cutoff=cut, Dmax=8)
+        assert np.array_equal(a.energy, b.energy) and np.array_equal(a.states, b.states)
+        assert np.array_equal(a.probability, b.probability) and a.degeneracy == b.degeneracy
+        assert a.discarded_probability == b.discarded_probability and a.negative_probability == b.negative_probability
+        assert a.stats['marginals'] == b.stats['marginals']

@@ -60,6 +60,8 @@ _SIGS = {
                                P, P, P, P, P, P, P, P, P, P, P, P, P]),
     'tn_row_shift': (c_int, [P, P, c_int, c_int, P]),
     'tn_sample': (c_int, [P, P, POINTER(TnSite), c_int, c_int, c_int, c_int, P, P, P, c_int, P, P, P, P]),
+    'tn_search_ground_state': (c_int, [P, P, c_int, c_int, P, P, P, P, c_int, c_double, c_double, P, P, P, P,
+                                       POINTER(c_int), POINTER(c_double), POINTER(c_double), POINTER(c_int64)]),
     'tn_sort_keys': (c_int, [P, P, P, P, P, c_int]),
     'tn_sort_capacity_for': (c_int, [c_int]),
     'tn_xor_diff': (c_int, [P, P, c_int, c_int, c_int, P, P, P, P, P, P, P, P]),

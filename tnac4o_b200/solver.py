@@ -69,6 +69,7 @@ class tnac4o:
         self._sites = None
         self._host = None
         self.native_rows = True      # boundary-MPS rows through the native driver (False: Python MPS methods)
+        self.native_search = True    # branch-and-bound loop through the native driver (False: the Python loop below)
         self.build_rhoT0 = False     # the reference also contracts the last row (rhoT[0] / rhoB[Ny]), which nothing reads
         if J is not None:
             self.J = upper_triangular(J, self.L)
@@ -447,6 +448,44 @@ class tnac4o:
         self.discarded_probability = _decode_ordered(ws['pdbits'].item())
         self.negative_probability = min(float(ws['gmin'].item()), 0)
 
+    def _native_search(self, M, relative_P_cutoff, min_dEng, t_rho, t0):
+        """the whole row / site loop of search_ground_state inside the library (csrc/search_native.cu): the same kernel
+        sequence as _setup_RR / _site_marginals / _site_step below, without the interpreter between launches"""
+        from ._native import TnSite
+        dev = self._dev()
+        c = Context.get(dev)
+        Nx, Ny = self.Nx, self.Ny
+        nsites = Nx * Ny
+        sites = self._site_tables()
+        site_arr = (TnSite * nsites)(*[sites[ny][nx].c for ny in range(Ny) for nx in range(Nx)])
+        ptrs, dims = [], []
+        for ny in range(Ny + 1):
+            psi = self.rhoT[ny]
+            ptrs += [0] * Nx if psi is None else [a.data_ptr() for a in psi.A]
+            dims += [0] * (Nx + 1) if psi is None else [psi.A[0].shape[0]] + [a.shape[2] for a in psi.A]
+        A_arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+        D_arr = (ctypes.c_int * len(dims))(*dims)
+        offs = np.concatenate([self._key_offsets(ny, nx) for ny in range(Ny) for nx in range(Nx)]).astype(np.uint8)
+        states = torch.empty((M, nsites), dtype=torch.uint8, device=dev)
+        Eng = torch.empty(M, dtype=F64, device=dev)
+        prob = torch.empty(M, dtype=F64, device=dev)
+        deg = torch.empty(M, dtype=torch.int64, device=dev)
+        n, pd, neg, marg = ctypes.c_int(0), ctypes.c_double(0.0), ctypes.c_double(0.0), ctypes.c_int64(0)
+        check(lib.tn_search_ground_state(c.handle, c.stream, Nx, Ny, site_arr, A_arr, D_arr,
+                                         offs.ctypes.data_as(ctypes.c_void_p), int(M), float(relative_P_cutoff),
+                                         float(min_dEng), ptr(states), ptr(Eng), ptr(prob), ptr(deg), ctypes.byref(n),
+                                         ctypes.byref(pd), ctypes.byref(neg), ctypes.byref(marg)))
+        n = n.value
+        self.stats['marginals'] = int(marg.value)
+        self.stats['seconds_rhoT'] = t_rho
+        self.stats['seconds_search'] = time.time() - t0
+        self.energy = Eng[:n].cpu().numpy()
+        self.degeneracy = int(deg[0].item())
+        self.states = states[:n].cpu().numpy().view(np.int8)[:, self.order]
+        self.probability = prob[:n].cpu().numpy()
+        self.discarded_probability = pd.value
+        self.negative_probability = min(neg.value, 0)
+
     def search_ground_state(self, M=2 ** 10, relative_P_cutoff=1e-6, min_dEng=1e-12, graduate_truncation=True,
                             Dmax=32, tolS=1e-16, tolV=1e-10, max_sweeps=20):
         """Branch-and-bound search for the most probable state (tnac4o.py:381-551).  Returns the energies."""
@@ -461,8 +500,12 @@ class tnac4o:
         t_rho = time.time() - t0
         self.logger.info('Elapsed: %.2f seconds', t_rho)
         t0 = time.time()
-        ws = self._alloc_search(M, int(np.max(self.N)), self._max_bond())
         self.logger.info('Searching ... ')
+        if self.native_search:
+            self._native_search(M, relative_P_cutoff, min_dEng, t_rho, t0)
+            self.logger.info('Elapsed search total: %.2f seconds', self.stats['seconds_rhoT'] + self.stats['seconds_search'])
+            return self.energy
+        ws = self._alloc_search(M, int(np.max(self.N)), self._max_bond())
         for ny in range(self.Ny):
             keep_time = time.time()
             self.logger.info('Row %d / %d', ny + 1, self.Ny)

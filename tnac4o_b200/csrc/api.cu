@@ -24,6 +24,11 @@ static std::mutex g_capture_mutex;
 void tn_capture_lock() { g_capture_mutex.lock(); }
 void tn_capture_unlock() { g_capture_mutex.unlock(); }
 
+cudaError_t tn_malloc_async(tn_ctx* ctx, void** p, size_t bytes, cudaStream_t st) {
+    if (ctx->pool) return cudaMallocFromPoolAsync(p, bytes, ctx->pool, st);
+    return cudaMallocAsync(p, bytes, st);
+}
+
 void* tn_scratch(tn_ctx* ctx, int slot, size_t bytes) {
     if (bytes <= ctx->scratch_bytes[slot]) return ctx->scratch[slot];
     if (ctx->capturing) {
@@ -65,16 +70,23 @@ int tn_create(int device, tn_ctx** out) {
         tn_set_error("tnac4o_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
         return TN_ERR_ARG;
     }
-    {
-        // temporaries of the native MPS driver come from the stream-ordered allocator: keep freed blocks cached
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            unsigned long long keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-    }
     tn_ctx* ctx = new tn_ctx();
     ctx->device = device;
+    {
+        // temporaries of the native drivers come from a stream-ordered pool owned by this context; freed blocks stay cached
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        if (cudaMemPoolCreate(&ctx->pool, &props) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        } else {
+            cudaGetLastError();
+            ctx->pool = nullptr;
+        }
+    }
     ctx->sm_count = prop.multiProcessorCount;
     cudaError_t e = cudaMallocHost(&ctx->pinned, 4096);
     if (e != cudaSuccess) {
@@ -96,6 +108,7 @@ int tn_destroy(tn_ctx* ctx) {
     for (int i = 0; i < tn_ctx::SLOTS; ++i)
         if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->pool) { cudaDeviceSynchronize(); cudaMemPoolDestroy(ctx->pool); }
     delete ctx;
     return TN_OK;
 }

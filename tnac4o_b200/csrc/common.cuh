@@ -16,12 +16,16 @@ struct tn_ctx {
     uint64_t scratch_gen = 0;         // bumped whenever a slot is reallocated (captured graphs hold slot pointers)
     bool capturing = false;           // a stream capture is in progress: slots must not be reallocated
     void* pinned = nullptr;           // small pinned host buffer for scalar read-backs
+    cudaMemPool_t pool = nullptr;     // private stream-ordered pool: no cross-stream reuse, hence no hidden dependencies
+                                      // between the streams of concurrent solver instances
     int64_t launches = 0;
 };
 
 void tn_set_error(const char* fmt, ...);
 int tn_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 enum { TN_SLOT_GEMM = 0, TN_SLOT_QR = 1, TN_SLOT_SVD = 2, TN_SLOT_SEARCH = 3, TN_SLOT_SORT = 4, TN_SLOT_MISC = 5, TN_SLOT_STAGE = 6 };
+// stream-ordered allocation from the context's private pool (temporaries of the native drivers)
+cudaError_t tn_malloc_async(tn_ctx* ctx, void** p, size_t bytes, cudaStream_t st);
 void* tn_scratch(tn_ctx* ctx, int slot, size_t bytes);   // returns nullptr (and sets the error) on failure
 // Process-wide lock that serialises stream captures against device-wide synchronising calls of other host threads
 // (scratch reallocation): cudaDeviceSynchronize / cudaFree fail while another thread's capture is open.

@@ -15,7 +15,8 @@ int tn_gemm_impl(tn_ctx* ctx, cudaStream_t st, int tA, int tB, int M, int N, int
 
 namespace {
 
-struct Scope;
+// the context whose pool serves the allocations of the calling host thread (one context per thread)
+thread_local tn_ctx* g_ctx = nullptr;
 
 // device buffer owned through the stream-ordered allocator
 struct Buf {
@@ -38,7 +39,7 @@ struct Buf {
     int alloc(int64_t count, cudaStream_t s) {
         release();
         st = s; n = count;
-        cudaError_t e = cudaMallocAsync((void**)&p, (size_t)(count > 0 ? count : 1) * sizeof(double), s);
+        cudaError_t e = tn_malloc_async(g_ctx, (void**)&p, (size_t)(count > 0 ? count : 1) * sizeof(double), s);
         if (e != cudaSuccess) { p = nullptr; return tn_cuda_fail(e, "cudaMallocAsync", __FILE__, __LINE__); }
         return TN_OK;
     }
@@ -339,6 +340,7 @@ int tn_row_compress(tn_ctx* ctx, void* stream, int L, const double* const* A_in,
                     double Dmax, double tolS, double tolV, int max_sweeps, int graduate, tn_row** out) {
     TN_REQUIRE(ctx && out && L >= 1, "bad arguments");
     cudaStream_t st = as_stream(stream);
+    g_ctx = ctx;
     tn_row* row = new tn_row();
     int rc = row->psi.init(ctx, st, L);
     for (int n = 0; n < L && !rc; ++n) {

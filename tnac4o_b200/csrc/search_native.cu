@@ -12,6 +12,8 @@ extern "C" int tn_sort_capacity_for(int n);
 
 namespace {
 
+thread_local tn_ctx* g_ctx = nullptr;
+
 struct DBuf {
     void* p = nullptr;
     cudaStream_t st = nullptr;
@@ -22,7 +24,7 @@ struct DBuf {
     int alloc(size_t bytes, cudaStream_t s) {
         if (p) cudaFreeAsync(p, st);
         st = s;
-        cudaError_t e = cudaMallocAsync(&p, bytes > 0 ? bytes : 1, s);
+        cudaError_t e = tn_malloc_async(g_ctx, &p, bytes > 0 ? bytes : 1, s);
         if (e != cudaSuccess) { p = nullptr; return tn_cuda_fail(e, "cudaMallocAsync", __FILE__, __LINE__); }
         return TN_OK;
     }
@@ -75,6 +77,7 @@ extern "C" int tn_search_ground_state(tn_ctx* ctx, void* stream, int Nx, int Ny,
                                       double* h_neg_min, long long* h_marginals) {
     TN_REQUIRE(ctx && sites && A && D && key_offsets && M >= 1 && Nx >= 1 && Ny >= 1, "bad arguments");
     cudaStream_t st = as_stream(stream);
+    g_ctx = ctx;
     const int nsites = Nx * Ny, vs = Nx + 1;
     int nsmax = 1, Dcap = 1, ndmax = 1;
     for (int i = 0; i < nsites; ++i) {

@@ -14,6 +14,8 @@ Fixtures
                       plus per-site traces (marginals of every branch, branch records after merge + top-M)
   ref_l512.npz        config 2: L=512 #1, M=2^10, Dmax=16
   ref_l2048.npz       config 4 (M=2^10 variant): L=2048 #1, Dmax=32
+  ref_l2048_m4096.npz config 4 as quoted: L=2048 #1, M=2^12, Dmax=32
+  ref_gibbs_l2048.npz config 5 at M=256 samples: L=2048 #1, beta=1, seed 1
   ref_l1152.npz       config 3: L=1152 #1 spectrum (ee=1, dE=1) -> number of decoded states, energies
 """
 import os
@@ -167,6 +169,18 @@ def make_big(L, D, M, name):
     np.savez_compressed(os.path.join(HERE, name), **out)
 
 
+def make_gibbs_l2048(M=256):
+    """config 5 at a CPU-feasible sample count: L=2048, beta=1, np.random.seed(1), Dmax=32"""
+    ins = ref.tnac4o(mode='Ising', Nx=16, Ny=16, Nc=8, J=droplet_J(2048, 1), beta=1)
+    np.random.seed(1)
+    t0 = time.time()
+    ins.gibbs_sampling(M=M, Dmax=32)
+    out = {'energy': ins.energy, 'states': ins.states.astype(np.int16), 'negative': np.float64(ins.negative_probability),
+           'seconds': np.float64(time.time() - t0), 'params': np.array([2048, 32, M], dtype=np.int64),
+           'energy_Jij': ref.energy_Jij(droplet_J(2048, 1), ins.binary_states())}
+    np.savez_compressed(os.path.join(HERE, 'ref_gibbs_l2048.npz'), **out)
+
+
 def make_l1152():
     ins = ref.tnac4o(mode='Ising', Nx=12, Ny=12, Nc=8, J=droplet_J(1152, 1), beta=3)
     t0 = time.time()
@@ -202,5 +216,7 @@ if __name__ == '__main__':
         {'instances': make_instances, 'small': make_small,
          'l512': lambda: make_big(512, 16, 1024, 'ref_l512.npz'),
          'l2048': lambda: make_big(2048, 32, 1024, 'ref_l2048.npz'),
+         'l2048m4096': lambda: make_big(2048, 32, 4096, 'ref_l2048_m4096.npz'),
+         'gibbs2048': make_gibbs_l2048,
          'l1152': make_l1152, 'j124': make_j124}[what]()
         print(what, 'done in %.1f s' % (time.time() - t0), flush=True)

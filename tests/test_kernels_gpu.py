@@ -218,3 +218,45 @@ def test_qr_graph_replay_on_side_stream():
         s.synchronize()
     assert torch.equal(Q0, Q1) and torch.equal(R0, R1) and int(b0.item()) == int(b1.item())
     _check_qr(A)
+
+
+@pytest.mark.parametrize('nb', [1, 63, 1000, 5000])
+@pytest.mark.parametrize('dims', [(32, 32, 16, 16, 16, 16), (32, 1, 16, 16, 1, 16), (8, 24, 16, 16, 16, 1), (5, 7, 3, 4, 2, 6)])
+def test_rr_level_grouped_gemm_against_einsum(nb, dims):
+    """tn_rr_level (tnac4o.py:1776-1782): RR'[b] = sum A[a,p,b'] RR[b][b',r] Wtr[l,p,r,u_b] / nfactor, every branch with
+    its own up index -- grouped by u, one DMMA GEMM per group tile, power-of-two scaling per branch"""
+    import ctypes
+    from tnac4o_b200._native import Context, TnSite, check, lib
+    Dl, Dr, nl, nd, nr, nu = dims
+    rng = np.random.default_rng(nb + Dl)
+    A = rng.standard_normal((Dl, nd, Dr))
+    W = rng.uniform(0.1, 1.0, size=(nu, nl, nd, nr))                      # [u][l][p][r] as SiteTables.WtrU
+    RR = rng.standard_normal((nb, Dr, nr)) * np.exp(rng.uniform(-30, 30, size=(nb, 1, 1)))
+    vind = rng.integers(0, nu, size=(nb, 5)).astype(np.uint8)
+    dA, dW, dRR, dv = up(A), up(W), up(RR), up(vind)
+    out = torch.empty((nb, Dl, nl), dtype=torch.float64, device=dev())
+    site = TnSite(1, nl, nd, nr, nu, None, dW.data_ptr(), None, None, None, None, None)
+    c = Context.get(dev())
+    check(lib.tn_rr_level(c.handle, c.stream, ctypes.byref(site), nb, Dl, Dr, dA.data_ptr(), dRR.data_ptr(),
+                          dv[:, 2:].data_ptr(), dv.stride(0), out.data_ptr()))
+    ref = np.einsum('apc,bcr,blpr->bal', A, RR, W[vind[:, 2]], optimize=True)
+    mx = np.abs(ref).reshape(nb, -1).max(axis=1)
+    ref /= (2.0 ** np.floor(np.log2(mx)))[:, None, None]
+    got = out.cpu().numpy()
+    assert np.max(np.abs(got - ref)) < 1e-12 * np.sqrt(Dr * nr * nd)
+    assert np.all(np.abs(got).reshape(nb, -1).max(axis=1) < 2.0) and np.all(np.abs(got).reshape(nb, -1).max(axis=1) >= 1.0)
+
+
+@pytest.mark.parametrize('k,decades', [(512, 6), (512, 10), (384, 4)])
+def test_svd_many_live_vectors_wide_cluster(k, decades):
+    """slowly decaying spectra (beta = 1 boundary MPS): 260-430 live vectors run in one 16-CTA cluster, more take the
+    multi-launch path; both must meet the same accuracy"""
+    rng = np.random.default_rng(k + decades)
+    U, _ = np.linalg.qr(rng.standard_normal((k, k)))
+    V, _ = np.linalg.qr(rng.standard_normal((k, k)))
+    s = np.logspace(0, -decades * 4, k)                 # about k * 4 / decades ... live vectors above eps
+    C = np.triu((U * s) @ V.T)
+    S = _check_svd(C)
+    exact = np.linalg.svd(C, compute_uv=False)
+    big = exact > 1e-9 * exact[0]
+    assert np.max(np.abs(S[big] / exact[big] - 1)) < 1e-6

@@ -196,6 +196,40 @@ def test_config4_L2048_M1024():
     np.testing.assert_allclose(ins.probability, z['gs_probability'], rtol=5e-6)
 
 
+def test_config4_L2048_M4096():
+    """BASELINE config 4 as quoted (M = 2^12, Dmax = 32) against the reference fixture ref_l2048_m4096.npz"""
+    import tnac4o_b200
+    z = golden('ref_l2048_m4096.npz')
+    J = droplet_couplings(2048)
+    ins = make(J, L=2048)
+    ins.search_ground_state(M=2 ** 12, relative_P_cutoff=1e-8, Dmax=32)
+    assert abs(ins.energy[0] - z['gs_energy'][0]) < 1e-9
+    assert int(ins.degeneracy) == int(z['gs_degeneracy']) == 2
+    bits = ins.binary_states()[0]
+    e_file, bits_file = droplet_golden(2048, 1)
+    assert min(int(np.sum(bits != z['gs_bits'][0])), int(np.sum(bits != bits_file))) == 0
+    assert abs(tnac4o_b200.energy_Jij(J, ins.binary_states())[0] - ins.energy[0]) < 1e-6
+    np.testing.assert_allclose(ins.probability, z['gs_probability'], rtol=5e-6)
+    assert abs(ins.discarded_probability - float(z['gs_discarded'])) < 1e-3
+    # number of conditional marginals evaluated = number of live branches summed over the sites (borderline
+    # candidates at the 1e-8 cut-off may differ by a few)
+    assert abs(ins.stats['marginals'] - int(z['marginals'])) <= 64
+
+
+def test_config5_gibbs_L2048_against_reference_samples():
+    """BASELINE config 5 at the sample count the reference finishes on a CPU (256): beta = 1, np.random.seed(1);
+    same uniforms => the same samples, state by state, and bit-identical energies"""
+    z = golden('ref_gibbs_l2048.npz')
+    J = droplet_couplings(2048)
+    ins = make(J, L=2048, beta=1)
+    np.random.seed(1)
+    ins.gibbs_sampling(M=256, Dmax=32)
+    same = np.all(ins.states == z['states'], axis=1)
+    assert same.mean() >= 0.98                               # identical draws up to 1e-9-level CDF ties
+    assert np.max(np.abs(ins.energy[same] - z['energy'][same])) < 1e-9
+    assert ins.negative_probability >= float(z['negative']) - 1e-9
+
+
 def test_j124_degeneracy_counting():
     """J124 C8 #1 (examples/test_examples.py:139-147): E = -2309 exactly, degeneracy 1152 -- exercises the merge rule"""
     z = golden('instances.npz')

@@ -57,7 +57,7 @@ template <int BM, int BN, int WM, int WN, bool AKC, bool BKC>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
 gemm_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, int lda, int64_t strideA,
             const double* __restrict__ B, int ldb, int64_t strideB, double beta, double* __restrict__ C, int ldc,
-            int64_t strideC, int splitk, int kchunk, double* __restrict__ partial) {
+            int64_t strideC, int splitk, int kchunk, double* __restrict__ partial, const int* __restrict__ bmap) {
     constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
     constexpr int THREADS = WARPS_M * WARPS_N * 32;
     constexpr int TM = WM / 8, TN = WN / 8;
@@ -76,8 +76,14 @@ gemm_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, int
     const int kend = min(K, kbeg + kchunk);
     const int ktiles = (kend > kbeg) ? (kend - kbeg + BK - 1) / BK : 0;
 
+    // grouped mode: batch entry z multiplies by B operand number bmap[z]; negative = unused entry
+    int bsel = batch;
+    if (bmap) {
+        bsel = bmap[batch];
+        if (bsel < 0) return;
+    }
     const double* Ab = A + batch * strideA + (AKC ? (int64_t)m0 * lda : (int64_t)m0);
-    const double* Bb = B + batch * strideB + (BKC ? (int64_t)n0 * ldb : (int64_t)n0);
+    const double* Bb = B + bsel * strideB + (BKC ? (int64_t)n0 * ldb : (int64_t)n0);
 
     double acc[TM][TN][2];
 #pragma unroll
@@ -161,7 +167,8 @@ __global__ void splitk_reduce_kernel(int M, int N, int splitk, int batch, const 
 
 template <int BM, int BN, int WM, int WN>
 int launch_cfg(tn_ctx* ctx, cudaStream_t st, int tA, int tB, int M, int N, int K, double alpha, const double* A, int lda,
-               int64_t sA, const double* B, int ldb, int64_t sB, double beta, double* C, int ldc, int64_t sC, int batch) {
+               int64_t sA, const double* B, int ldb, int64_t sB, double beta, double* C, int ldc, int64_t sC, int batch,
+               const int* bmap = nullptr) {
     constexpr int THREADS = (BM / WM) * (BN / WN) * 32;
     const bool akc = !tA, bkc = tB;
     size_t smem = 0;
@@ -172,7 +179,7 @@ int launch_cfg(tn_ctx* ctx, cudaStream_t st, int tA, int tB, int M, int N, int K
     }
     int tiles = ceil_div(M, BM) * ceil_div(N, BN) * batch;
     int splitk = 1;
-    if (tiles * 2 <= ctx->sm_count && K >= 512) {
+    if (tiles * 2 <= ctx->sm_count && K >= 512 && !bmap) {
         splitk = min(min(ctx->sm_count / tiles, K / 256), 32);
         if (splitk < 1) splitk = 1;
     }
@@ -189,7 +196,7 @@ int launch_cfg(tn_ctx* ctx, cudaStream_t st, int tA, int tB, int M, int N, int K
         auto kern = gemm_kernel<BM, BN, WM, WN, AK, BKc>;                                                              \
         TN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
         kern<<<grid, THREADS, smem, st>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, splitk, kchunk,    \
-                                          partial);                                                                    \
+                                          partial, bmap);                                                              \
     } while (0)
     if (akc && bkc) TN_GEMM_LAUNCH(true, true);
     else if (akc && !bkc) TN_GEMM_LAUNCH(true, false);
@@ -219,6 +226,23 @@ int tn_gemm_impl(tn_ctx* ctx, cudaStream_t st, int tA, int tB, int M, int N, int
     if (big_tiles >= ctx->sm_count && M >= 128 && N >= 128)
         return launch_cfg<128, 128, 32, 64>(ctx, st, tA, tB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
     return launch_cfg<64, 64, 32, 32>(ctx, st, tA, tB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
+}
+
+// Grouped GEMM (search.cu): ntiles row tiles of `tile_rows` rows each; tile z computes
+//   C[z * tile_rows ..][0:N] = X[z * tile_rows ..][0:K] . B_{bmap[z]} (K x N, row-major),  bmap[z] < 0 = skip.
+// No split-K: every output row is accumulated in ascending k whatever the tile configuration, so a row's result does
+// not depend on how many other rows are in the call.
+int tn_gemm_grouped_impl(tn_ctx* ctx, cudaStream_t st, int tile_rows, int ntiles, int N, int K, const double* X, int ldx,
+                         const double* B, int ldb, int64_t strideB, const int* bmap, double* C, int ldc) {
+    if (ntiles <= 0 || N <= 0) return TN_OK;
+    if (tile_rows == 128)
+        return launch_cfg<128, 128, 32, 64>(ctx, st, 0, 0, 128, N, K, 1.0, X, ldx, (int64_t)128 * ldx, B, ldb, strideB, 0.0, C,
+                                            ldc, (int64_t)128 * ldc, ntiles, bmap);
+    if (tile_rows == 64)
+        return launch_cfg<64, 64, 32, 32>(ctx, st, 0, 0, 64, N, K, 1.0, X, ldx, (int64_t)64 * ldx, B, ldb, strideB, 0.0, C, ldc,
+                                          (int64_t)64 * ldc, ntiles, bmap);
+    tn_set_error("grouped GEMM: tile_rows must be 64 or 128");
+    return TN_ERR_ARG;
 }
 
 extern "C" int tn_gemm(tn_ctx* ctx, void* stream, int transA, int transB, int M, int N, int K, double alpha,

@@ -5,6 +5,8 @@
 
 int tn_sort3_impl(tn_ctx* ctx, cudaStream_t st, unsigned long long* hi, unsigned long long* lo, unsigned long long* tie, int n);
 int tn_scan_impl(tn_ctx* ctx, cudaStream_t st, const int* in, int* out, int n, int* tmp);
+int tn_gemm_grouped_impl(tn_ctx* ctx, cudaStream_t st, int tile_rows, int ntiles, int N, int K, const double* X, int ldx,
+                         const double* B, int ldb, int64_t strideB, const int* bmap, double* C, int ldc);
 
 namespace {
 
@@ -69,6 +71,82 @@ rr_level_kernel(int nb, int Dl, int Dr, int nl, int nd, int nr, int nu, const do
             RRout[(int64_t)b * Dl * nl + o] = s * inv;
             cnt++;
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same level as ONE contraction on the DMMA path.  With the MPS tensor and the traced PEPS tensor contracted
+// first (once per level, not per branch),
+//   AW_u[(b', r)][(a, l)] = sum_p A[a][p][b'] Wtr[l][p][r][u],
+// the level is  RRout_b[(a, l)] = sum_{(b', r)} RRin_b[(b', r)] AW_{u_b}[(b', r)][(a, l)]: a row-vector times one of nu
+// matrices.  Branches are grouped by their up index u_b (rows padded to whole GEMM tiles), multiplied by their
+// group's matrix with the grouped GEMM, and scattered back with the per-branch nfactor scaling.
+// 2 Dr nr Dl nl flop per branch-level (524 288 at D = 32) instead of 786 432, at tensor-core rates.
+__global__ void rr_aw_kernel(int Dl, int Dr, int nl, int nd, int nr, int nu, const double* __restrict__ A,
+                             const double* __restrict__ WtrU, double* __restrict__ AW) {
+    const int K = Dr * nr, N = Dl * nl;
+    const int64_t total = (int64_t)nu * K * N;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i % N), k = (int)((i / N) % K), u = (int)(i / ((int64_t)N * K));
+        const int a = n / nl, l = n % nl, bp = k / nr, r = k % nr;
+        const double* ap = A + (int64_t)a * nd * Dr + bp;
+        const double* wp = WtrU + ((int64_t)u * nl + l) * nd * nr + r;
+        double s = 0.0;
+        for (int p = 0; p < nd; ++p) s += ap[(int64_t)p * Dr] * wp[(int64_t)p * nr];
+        AW[i] = s;
+    }
+}
+
+// one CTA: group sizes by up index, tile-padded group offsets, tile -> group map, destination row of every branch
+// (the order inside a group is arbitrary: a row's product does not depend on where the row sits)
+__global__ void __launch_bounds__(1024)
+rr_group_kernel(int nb, int nu, int tile, int ntiles, const uint8_t* __restrict__ up, int up_stride, int* __restrict__ pos,
+                int* __restrict__ bmap) {
+    __shared__ int cnt[256], off[256], cur[256];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 256; i += blockDim.x) { cnt[i] = 0; cur[i] = 0; off[i] = 0; }
+    __syncthreads();
+    for (int b = tid; b < nb; b += blockDim.x) atomicAdd(&cnt[up[(int64_t)b * up_stride]], 1);
+    __syncthreads();
+    if (tid == 0) {
+        int o = 0;
+        for (int u = 0; u < nu; ++u) { off[u] = o; o += (cnt[u] + tile - 1) / tile * tile; }
+    }
+    __syncthreads();
+    for (int t = tid; t < ntiles; t += blockDim.x) {
+        const int row = t * tile;
+        int g = -1;
+        for (int u = 0; u < nu; ++u)
+            if (cnt[u] > 0 && row >= off[u] && row < off[u] + (cnt[u] + tile - 1) / tile * tile) g = u;
+        bmap[t] = g;
+    }
+    for (int b = tid; b < nb; b += blockDim.x) {
+        const int u = up[(int64_t)b * up_stride];
+        pos[b] = off[u] + atomicAdd(&cur[u], 1);
+    }
+}
+
+__global__ void rr_gather_kernel(int nb, int K, const double* __restrict__ RRin, const int* __restrict__ pos,
+                                 double* __restrict__ X) {
+    const int64_t total = (int64_t)nb * K;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / K), k = (int)(i % K);
+        X[(int64_t)pos[b] * K + k] = RRin[i];
+    }
+}
+
+// RRout[b] = C[pos[b]] / nfactor(C[pos[b]]) -- one warp per branch, same exponent rule as rr_level_kernel
+__global__ void __launch_bounds__(256)
+rr_scatter_kernel(int nb, int N, const double* __restrict__ C, const int* __restrict__ pos, double* __restrict__ RRout) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int b = blockIdx.x * wpb + (threadIdx.x >> 5); b < nb; b += gridDim.x * wpb) {
+        const double* row = C + (int64_t)pos[b] * N;
+        double mx = 0.0;
+        for (int i = lane; i < N; i += 32) mx = fmax(mx, fabs(row[i]));
+        mx = warp_max(mx);
+        const double inv = ldexp(1.0, 1023 - (int)((((unsigned long long)__double_as_longlong(mx)) >> 52) & 0x7ff));
+        for (int i = lane; i < N; i += 32) RRout[(int64_t)b * N + i] = row[i] * inv;
     }
 }
 
@@ -374,6 +452,43 @@ int tn_rr_level(tn_ctx* ctx, void* stream, const tn_site* site, int nb, int Dl, 
                 const double* RRin, const uint8_t* up, int up_stride, double* RRout) {
     TN_REQUIRE(ctx && site && nb >= 0, "bad arguments");
     if (nb == 0) return TN_OK;
+    {
+        const int K = Dr * site->nr, N = Dl * site->nl, nu = site->nu;
+        const size_t aw_bytes = (size_t)nu * K * N * sizeof(double);
+        if (nu <= 256 && aw_bytes <= ((size_t)512 << 20)) {
+            cudaStream_t st = as_stream(stream);
+            const int tile = nb >= 4096 ? 128 : 64;
+            const int ntiles = ceil_div(nb, tile) + nu;
+            const size_t rows = (size_t)ntiles * tile;
+            // one stream-ordered block: AW | X | C | pos | bmap
+            const size_t nd_ = ((size_t)nu * K * N + rows * K + rows * N) * sizeof(double);
+            const size_t ni_ = ((size_t)nb + ntiles) * sizeof(int);
+            void* blk = nullptr;
+            TN_CUDA(tn_malloc_async(ctx, &blk, nd_ + ni_, st));
+            double* AW = (double*)blk;
+            double* X = AW + (size_t)nu * K * N;
+            double* C = X + rows * K;
+            int* pos = (int*)(C + rows * N);
+            int* bmap = pos + nb;
+            const int cap = 8 * ctx->sm_count;
+            int64_t want = ((int64_t)nu * K * N + 255) / 256;
+            rr_aw_kernel<<<(int)(want < cap ? want : cap), 256, 0, st>>>(Dl, Dr, site->nl, site->nd, site->nr, nu, A, site->Wtr, AW);
+            TN_LAUNCHED(ctx);
+            rr_group_kernel<<<1, 1024, 0, st>>>(nb, nu, tile, ntiles, up, up_stride, pos, bmap);
+            TN_LAUNCHED(ctx);
+            want = ((int64_t)nb * K + 255) / 256;
+            rr_gather_kernel<<<(int)(want < cap ? want : cap), 256, 0, st>>>(nb, K, RRin, pos, X);
+            TN_LAUNCHED(ctx);
+            int rc = tn_gemm_grouped_impl(ctx, st, tile, ntiles, N, K, X, K, AW, N, (int64_t)K * N, bmap, C, N);
+            if (rc) { cudaFreeAsync(blk, st); return rc; }
+            want = (nb + 7) / 8;
+            rr_scatter_kernel<<<(int)(want < cap ? want : cap), 256, 0, st>>>(nb, N, C, pos, RRout);
+            TN_LAUNCHED(ctx);
+            TN_CUDA(cudaFreeAsync(blk, st));
+            return TN_OK;
+        }
+    }
+    // fall-back for very wide up legs: one CTA per branch on the CUDA cores
     size_t smem = ((size_t)site->nd * Dr * (site->nl + 1) + (size_t)Dr * site->nr) * sizeof(double);
     TN_REQUIRE(smem <= 220 * 1024, "bond dimension too large for rr_level shared memory");
     // a fixed maximum: concurrent host threads must not lower the attribute under each other's launches

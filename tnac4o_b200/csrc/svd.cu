@@ -17,6 +17,8 @@
 // orthogonalised -- for a triangular factor that is the graded side, typically 100-200 of 512.
 #include <cooperative_groups.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -186,22 +188,24 @@ jacobi_round_kernel(double* __restrict__ E, int ldw, int a, int nc, int bsz, int
 // sends it to the pair's owner CTA through DSMEM, (2) the owner sums the 8 partials in a fixed order, decides the
 // rotation and broadcasts (c, s), (3) every CTA rotates its slices.  Two cluster barriers per round and no kernel
 // launch or host read-back until convergence.
-constexpr int CLJ = 8;
+constexpr int CLJ = 8;                                // portable cluster size
+constexpr int CLJ_MAX = 16;                           // opt-in (non-portable) size: twice the shared memory, half the traffic per CTA
 constexpr int CJ_MAXPAIRS = 256;                      // nc <= 512
 constexpr int CJ_MAXOWN = CJ_MAXPAIRS / CLJ;
 
-__global__ void __cluster_dims__(CLJ, 1, 1) __launch_bounds__(JT, 1)
+__global__ void __launch_bounds__(JT, 1)
 jacobi_cluster_kernel(double* __restrict__ E, int ldw, int a, int ext, int nc, int max_sweeps, double tol,
                       const SvdMeta* __restrict__ meta, int* __restrict__ status /* [0] = sweeps, [1] = converged */) {
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
+    const int ncl = (int)cluster.num_blocks();        // 8 or 16 (launch attribute)
     extern __shared__ __align__(16) double Sl[];      // [nc][ll]
-    __shared__ double part[CLJ][CJ_MAXOWN][3];
+    __shared__ double part[CLJ_MAX][CJ_MAXOWN][3];
     __shared__ double rot[CJ_MAXPAIRS][2];
-    __shared__ unsigned int cnt[2][CLJ];
+    __shared__ unsigned int cnt[2][CLJ_MAX];
     __shared__ unsigned int myrot;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int aw = (a + CLJ - 1) / CLJ, ej = (ext + CLJ - 1) / CLJ, ll = aw + ej;
+    const int aw = (a + ncl - 1) / ncl, ej = (ext + ncl - 1) / ncl, ll = aw + ej;
     const int wlo = rank * aw, jlo = rank * ej;
     const double floor2 = DEAD_FLOOR * DEAD_FLOOR * meta->fro2;
     for (int64_t i = tid; i < (int64_t)nc * ll; i += JT) {
@@ -244,18 +248,17 @@ jacobi_cluster_kernel(double* __restrict__ E, int ldw, int a, int ext, int nc, i
                     apq += __shfl_xor_sync(0xffffffffu, apq, o);
                 }
                 if (sub == 0 && i < half) {
-                    double* dst = cluster.map_shared_rank(&part[rank][i / CLJ][0], i % CLJ);
+                    double* dst = cluster.map_shared_rank(&part[rank][i / ncl][0], i % ncl);
                     dst[0] = app; dst[1] = aqq; dst[2] = apq;
                 }
             }
             cluster.sync();
             // ---- (2) owners decide the rotations and broadcast them
             {
-                int i = tid * CLJ + rank;                          // pairs owned by this CTA: i % CLJ == rank
+                int i = tid * ncl + rank;                          // pairs owned by this CTA: i % ncl == rank
                 if (tid < CJ_MAXOWN && i < half) {
                     double app = 0.0, aqq = 0.0, apq = 0.0;
-#pragma unroll
-                    for (int src = 0; src < CLJ; ++src) { app += part[src][tid][0]; aqq += part[src][tid][1]; apq += part[src][tid][2]; }
+                    for (int src = 0; src < ncl; ++src) { app += part[src][tid][0]; aqq += part[src][tid][1]; apq += part[src][tid][2]; }
                     double cs = 1.0, sn = 0.0;
                     if (fabs(apq) > tol * sqrt(app) * sqrt(aqq) && app > floor2 && aqq > floor2) {
                         double zeta = (aqq - app) / (2.0 * apq);
@@ -264,8 +267,7 @@ jacobi_cluster_kernel(double* __restrict__ E, int ldw, int a, int ext, int nc, i
                         sn = cs * t;
                         atomicAdd(&myrot, 1u);
                     }
-#pragma unroll
-                    for (int dstc = 0; dstc < CLJ; ++dstc) {
+                    for (int dstc = 0; dstc < ncl; ++dstc) {
                         double* dst = cluster.map_shared_rank(&rot[i][0], dstc);
                         dst[0] = cs; dst[1] = sn;
                     }
@@ -292,14 +294,13 @@ jacobi_cluster_kernel(double* __restrict__ E, int ldw, int a, int ext, int nc, i
         }
         // ---- end of sweep: all CTAs learn the total number of rotations
         const int buf = sweep & 1;
-        if (tid < CLJ) {
+        if (tid < ncl) {
             unsigned int* dst = cluster.map_shared_rank(&cnt[buf][rank], tid);
             *dst = myrot;
         }
         cluster.sync();
         unsigned int total = 0;
-#pragma unroll
-        for (int src = 0; src < CLJ; ++src) total += cnt[buf][src];
+        for (int src = 0; src < ncl; ++src) total += cnt[buf][src];
         __syncthreads();
         if (tid == 0) myrot = 0;
         __syncthreads();
@@ -383,6 +384,43 @@ __global__ void truncation_rank_kernel(const double* __restrict__ S, int k, doub
 
 }  // namespace
 
+// 0 = portable 8-CTA clusters only, 1 = 16-CTA clusters where 8 do not fit (default), 2 = also prefer 16 CTAs for
+// every problem with >= 96 live vectors (environment TN_SVD_WIDE = 0 / 1 / 2, read once)
+static int wide_clusters() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("TN_SVD_WIDE");
+        mode = (e && e[0] >= '0' && e[0] <= '2') ? (e[0] - '0') : 1;
+    }
+    return mode;
+}
+
+// can this device co-schedule one 16-CTA cluster of the Jacobi kernel at its largest shared-memory footprint?
+static bool wide_launchable() {
+    static int ok = -1;
+    if (ok < 0) {
+        const size_t CL_SMEM = 210 * 1024;
+        cudaFuncSetAttribute(jacobi_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CL_SMEM);
+        cudaFuncSetAttribute(jacobi_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(16, 1, 1);
+        cfg.blockDim = dim3(JT, 1, 1);
+        cfg.dynamicSmemBytes = CL_SMEM;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 16;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int n = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&n, jacobi_cluster_kernel, &cfg);
+        if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+        ok = n > 0 ? 1 : 0;
+    }
+    return ok == 1;
+}
+
 extern "C" int tn_svd(tn_ctx* ctx, void* stream, int m, int n, const double* C, int ldc, double* U, int ldu, double* S,
                       double* Vt, int ldvt, int want_vectors, int* h_sweeps) {
     TN_REQUIRE(ctx != nullptr, "null context");
@@ -407,8 +445,8 @@ extern "C" int tn_svd(tn_ctx* ctx, void* stream, int m, int n, const double* C, 
     const int a = (m < n) ? n : m;
     // small problems: everything resident in one CTA or one cluster without deflation -> no host read-back
     const size_t CL_SMEM = 210 * 1024;
-    auto cluster_fits = [&](int nvec, int e) {
-        size_t ll = (size_t)ceil_div(a, CLJ) + (size_t)ceil_div(e, CLJ);
+    auto cluster_fits = [&](int nvec, int e, int ncl = CLJ) {
+        size_t ll = (size_t)ceil_div(a, ncl) + (size_t)ceil_div(e, ncl);
         return nvec >= 2 && nvec <= 2 * CJ_MAXPAIRS && (size_t)nvec * ll * sizeof(double) <= CL_SMEM;
     };
     const int ext_full = want_vectors ? kfull : 0;
@@ -470,12 +508,28 @@ extern "C" int tn_svd(tn_ctx* ctx, void* stream, int m, int n, const double* C, 
             TN_LAUNCHED(ctx);
         }
         sweeps = 1;
-    } else if (cluster_fits(nc, ext)) {
-        // cluster-resident: one launch, no host read-back inside the iteration
-        size_t ll = (size_t)ceil_div(a, CLJ) + (size_t)ceil_div(ext, CLJ);
+    } else if (cluster_fits(nc, ext) || (wide_clusters() && wide_launchable() && cluster_fits(nc, ext, CLJ_MAX))) {
+        // cluster-resident: one launch, no host read-back inside the iteration.  8 CTAs when the live vectors fit,
+        // 16 (non-portable cluster size) for the larger problems that would otherwise take the multi-launch path
+        const int ncl = (cluster_fits(nc, ext) && !(wide_clusters() == 2 && wide_launchable() && nc >= 96 && cluster_fits(nc, ext, CLJ_MAX)))
+                            ? CLJ : CLJ_MAX;
+        size_t ll = (size_t)ceil_div(a, ncl) + (size_t)ceil_div(ext, ncl);
         size_t smem = (size_t)nc * ll * sizeof(double);
         TN_CUDA(cudaFuncSetAttribute(jacobi_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CL_SMEM));
-        jacobi_cluster_kernel<<<CLJ, JT, smem, st>>>(E, ldw, a, ext, nc, MAX_SWEEPS, tol, meta, status);
+        TN_CUDA(cudaFuncSetAttribute(jacobi_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(ncl, 1, 1);
+        cfg.blockDim = dim3(JT, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = ncl;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        TN_CUDA(cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel, E, ldw, a, ext, nc, (int)MAX_SWEEPS, tol, (const SvdMeta*)meta, status));
         TN_LAUNCHED(ctx);
         sweeps = -1;
         if (!small) {

@@ -1,6 +1,12 @@
-"""Multi-GPU plumbing (one process per GPU, torch.distributed).  The contraction path shards by independent units --
-instances (ground-state search) or samples (Gibbs sampling) -- so there is no data-path collective: ranks only agree
-on the partition and gather results at the end."""
+"""Multi-GPU plumbing (one process per GPU, torch.distributed over NCCL).
+
+Three ways the contraction path spreads over GPUs:
+  * independent instances / rotations: replicas, no data-path collective (bench.py --gpus N);
+  * Gibbs samples: every rank draws the same uniforms and keeps its slice (:class:`UniformStream`), results are
+    gathered once at the end (:func:`gather_samples`);
+  * the branch batch of ONE search: :class:`BranchShards` -- every rank evaluates the right environments and the
+    conditional marginals of its slice of the live branches, the candidate log-probabilities are all-gathered, and
+    the selection (cut-off, merge, global top-M) runs replicated and deterministic on every rank."""
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -45,6 +51,88 @@ def gather_samples(energy, states):
     parts = [None] * world
     dist.all_gather_object(parts, (np.asarray(energy), np.asarray(states)))
     return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts], axis=0)
+
+
+_SIGN = -2 ** 63
+
+
+class BranchShards:
+    """Slice of the live branches owned by this rank plus the collectives of one site of the branch-and-bound.
+
+    Branch records (vind, states, Eng, prob, deg, RL) and the boundary MPS are replicated; the work that scales with
+    the number of branches -- right environments (tn_rr_level) and conditional marginals (tn_gemm + tn_marginals) --
+    is sharded by contiguous, equally sized chunks of rows (the last chunk may be short or empty).  Buffers that are
+    gathered must have room for ``padded(B)`` rows."""
+
+    def __init__(self, group=None, stage_through_host=None):
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        # NCCL moves device buffers directly; any other backend (gloo in the single-GPU tests) goes through the host
+        self.host = (dist.get_backend(group) != 'nccl') if stage_through_host is None else bool(stage_through_host)
+        self.bytes_gathered = 0
+
+    def chunk(self, B):
+        return -(-int(B) // self.world)
+
+    def padded(self, B):
+        return self.chunk(B) * self.world
+
+    def slice(self, B):
+        c = self.chunk(B)
+        lo = min(self.rank * c, int(B))
+        return lo, min(lo + c, int(B))
+
+    def allgather_rows(self, buf, B):
+        """buf (rows >= padded(B), ...) holds this rank's rows [lo, hi); afterwards every rank holds rows [0, B)"""
+        c = self.chunk(B)
+        full = buf[:c * self.world]
+        mine = full[self.rank * c:(self.rank + 1) * c]
+        self.bytes_gathered += full.numel() * full.element_size()
+        if self.host and full.is_cuda:
+            out = torch.empty(full.shape, dtype=full.dtype)
+            dist.all_gather_into_tensor(out, mine.cpu().contiguous(), group=self.group)
+            full.copy_(out)
+        else:
+            dist.all_gather_into_tensor(full, mine.clone(), group=self.group)
+        return buf
+
+    def _allreduce(self, t, op):
+        if self.host and t.is_cuda:
+            h = t.cpu()
+            dist.all_reduce(h, op=op, group=self.group)
+            t.copy_(h)
+        else:
+            dist.all_reduce(t, op=op, group=self.group)
+        return t
+
+    def allreduce_max_ordered_(self, bits):
+        """max over ranks of an int64 tensor that holds order-preserving *unsigned* encodings (common.cuh:
+        ordered_bits); flipping the top bit turns the unsigned order into int64 order"""
+        t = torch.bitwise_xor(bits, _SIGN)
+        self._allreduce(t, dist.ReduceOp.MAX)
+        bits.copy_(torch.bitwise_xor(t, _SIGN))
+        return bits
+
+    def allreduce_min_(self, t):
+        return self._allreduce(t, dist.ReduceOp.MIN)
+
+    def allreduce_sum_(self, t):
+        return self._allreduce(t, dist.ReduceOp.SUM)
+
+    def broadcast_(self, t, src=0):
+        if self.host and t.is_cuda:
+            h = t.cpu()
+            dist.broadcast(h, src=src, group=self.group)
+            t.copy_(h)
+        else:
+            dist.broadcast(t, src=src, group=self.group)
+        return t
+
+    def same_everywhere(self, obj):
+        """True when every rank passes an equal (picklable) object"""
+        parts = [None] * self.world
+        dist.all_gather_object(parts, obj, group=self.group)
+        return all(p == parts[0] for p in parts)
 
 
 class UniformStream:

@@ -327,16 +327,17 @@ class tnac4o:
             self.RL = torch.ones((cap * Dcap,), dtype=F64, device=dev)
             self.n = 1
 
-    def _alloc_search(self, cap, nsmax, Dcap):
+    def _alloc_search(self, cap, nsmax, Dcap, shards=None):
         dev = self._dev()
         nsites = self.Nx * self.Ny
-        ws = {}
+        ws = {'shards': shards}
         ws['cur'] = self._Branches(cap, self.Nx, nsites, Dcap, dev)
         ws['nxt'] = self._Branches(cap, self.Nx, nsites, Dcap, dev)
         ncand = cap * nsmax
         kcap = ops.sort_capacity(ncand)
-        ws['cand'] = torch.empty(ncand, dtype=F64, device=dev)
-        ws['flag'] = torch.empty(cap, dtype=F64, device=dev)
+        pad = 0 if shards is None else shards.world        # gathered buffers hold world equal chunks (parallel.BranchShards)
+        ws['cand'] = torch.empty((cap + pad) * nsmax, dtype=F64, device=dev)
+        ws['flag'] = torch.empty(cap + pad, dtype=F64, device=dev)
         ws['surv'] = torch.empty(ncand, dtype=torch.int32, device=dev)
         for name in ('khi', 'klo', 'ktie'):
             ws[name] = torch.empty(kcap, dtype=torch.int64, device=dev)
@@ -351,23 +352,30 @@ class tnac4o:
         ws['gmin'] = torch.zeros(1, dtype=F64, device=dev)
         return ws
 
-    def _setup_RR(self, br, ny):
+    def _setup_RR(self, br, ny, shards=None):
         """right environments of row ny for every row-start branch, all levels (tnac4o.py:1768-1784).
-        RRat[nx] covers sites nx..Nx-1; site nx of the search uses RRat[nx + 1]."""
+        RRat[nx] covers sites nx..Nx-1; site nx of the search uses RRat[nx + 1].  With ``shards`` every rank
+        contracts the levels of its own slice of branches and the levels are all-gathered at the end of the row
+        set-up (a branch met later in the row may descend from any row-start branch)."""
         dev = self._dev()
         c = Context.get(dev)
         sites = self._site_tables()[ny]
         A = self.rhoT[ny + 1].A
         nb = br.n
+        lo, hi, rows = (0, nb, nb) if shards is None else (*shards.slice(nb), shards.padded(nb))
         RRat = [None] * (self.Nx + 1)
-        RRat[self.Nx] = torch.ones((nb, 1, 1), dtype=F64, device=dev)
+        RRat[self.Nx] = torch.ones((rows, 1, 1), dtype=F64, device=dev)
         for nx in range(self.Nx - 1, 0, -1):
             Dl, nd, Dr = A[nx].shape
-            out = torch.empty((nb, Dl, sites[nx].nl), dtype=F64, device=dev)
-            up = br.vind[:, nx + 1:]
-            check(lib.tn_rr_level(c.handle, c.stream, sites[nx].ref, nb, Dl, Dr, ptr(A[nx]), ptr(RRat[nx + 1]),
-                                  up.data_ptr(), br.vind.stride(0), ptr(out)))
+            out = torch.empty((rows, Dl, sites[nx].nl), dtype=F64, device=dev)
+            if hi > lo:
+                up = br.vind[lo:, nx + 1:]
+                check(lib.tn_rr_level(c.handle, c.stream, sites[nx].ref, hi - lo, Dl, Dr, ptr(A[nx]), ptr(RRat[nx + 1][lo:]),
+                                      up.data_ptr(), br.vind.stride(0), ptr(out[lo:])))
             RRat[nx] = out
+        if shards is not None:
+            for nx in range(self.Nx - 1, 0, -1):
+                shards.allgather_rows(RRat[nx], nb)
         br.root[:nb] = torch.arange(nb, dtype=torch.int32, device=dev)
         return RRat
 
@@ -379,6 +387,9 @@ class tnac4o:
         A = self.rhoT[ny + 1].A[nx]
         Dl, nd, Dr = A.shape
         B = br.n
+        shards = ws.get('shards')
+        if shards is not None:
+            return self._site_marginals_sharded(ws, br, RRat, site, A, nx, shards)
         T1 = ops.gemm(br.RL[:B * Dl].view(B, Dl), A.view(Dl, nd * Dr))
         P = torch.empty((B, site.nS), dtype=F64, device=dev) if want_P else None
         cand = None if want_P == 'only' else ws['cand']
@@ -388,6 +399,29 @@ class tnac4o:
         ws['gmin'] = torch.minimum(ws['gmin'], ws['flag'][:B].min())
         self.stats['marginals'] = self.stats.get('marginals', 0) + B
         return P
+
+    def _site_marginals_sharded(self, ws, br, RRat, site, A, nx, shards):
+        """the same kernels on this rank's slice [lo, hi) of the branches, then the exchange step of the site
+        (SURVEY.md section 8e): all-gather of the candidate log-probabilities cand[b][s] and max over ranks of the
+        best candidate, after which every rank holds what the single-GPU path holds at this point."""
+        c = Context.get(self._dev())
+        Dl, nd, Dr = A.shape
+        B = br.n
+        lo, hi = shards.slice(B)
+        nS = site.nS
+        if hi > lo:
+            T1 = ops.gemm(br.RL[:B * Dl].view(B, Dl)[lo:hi], A.view(Dl, nd * Dr))
+            check(lib.tn_marginals(c.handle, c.stream, site.ref, hi - lo, Dr, ptr(T1), ptr(RRat[nx + 1]), ptr(br.root[lo:]),
+                                   ptr(br.vind[lo:]), br.vind.stride(0), nx, ptr(br.prob[lo:]), ptr(ws['cand'][lo * nS:]),
+                                   ptr(ws['flag'][lo:]), ptr(ws['maxbits']), None))
+            ws['gmin'] = torch.minimum(ws['gmin'], ws['flag'][lo:hi].min())
+        else:
+            ws['maxbits'].zero_()                      # the smallest ordered encoding: this rank contributes nothing
+        rows = shards.padded(B)
+        shards.allgather_rows(ws['cand'][:rows * nS].view(rows, nS), B)
+        shards.allreduce_max_ordered_(ws['maxbits'])
+        self.stats['marginals'] = self.stats.get('marginals', 0) + (hi - lo)
+        return None
 
     def _site_step(self, ws, RRat, ny, nx, M, relative_P_cutoff, min_dEng):
         """one site of the branch-and-bound: select -> expand -> merge -> top-M -> materialise (tnac4o.py:456-535)"""
@@ -437,6 +471,13 @@ class tnac4o:
     def _finish_search(self, ws, t_rho, t0):
         br = ws['cur']
         n = br.n
+        shards = ws.get('shards')
+        if shards is not None:
+            shards.allreduce_min_(ws['gmin'])
+            self.stats['marginals_this_rank'] = self.stats.get('marginals', 0)
+            tot = torch.tensor([float(self.stats.get('marginals', 0))], dtype=F64, device=self._dev())
+            self.stats['marginals'] = int(shards.allreduce_sum_(tot).item())
+            self.stats['bytes_gathered'] = shards.bytes_gathered
         torch.cuda.current_stream(self._dev()).synchronize()
         self.stats['seconds_rhoT'] = t_rho
         self.stats['seconds_search'] = time.time() - t0
@@ -486,9 +527,24 @@ class tnac4o:
         self.discarded_probability = pd.value
         self.negative_probability = min(neg.value, 0)
 
+    def _replicate_rhoT(self, shards):
+        """Right environments are replicated: every rank builds the boundary MPS with the same
+        deterministic kernels; rank 0's tensors are then broadcast so that the replicas are identical by construction."""
+        shapes = [None if psi is None else [tuple(a.shape) for a in psi.A] for psi in self.rhoT]
+        if not shards.same_everywhere(shapes):
+            raise RuntimeError('boundary MPS bond dimensions differ between ranks')
+        for psi in self.rhoT:
+            if psi is not None:
+                for a in psi.A:
+                    shards.broadcast_(a, src=0)
+
     def search_ground_state(self, M=2 ** 10, relative_P_cutoff=1e-6, min_dEng=1e-12, graduate_truncation=True,
-                            Dmax=32, tolS=1e-16, tolV=1e-10, max_sweeps=20):
-        """Branch-and-bound search for the most probable state (tnac4o.py:381-551).  Returns the energies."""
+                            Dmax=32, tolS=1e-16, tolV=1e-10, max_sweeps=20, shards=None):
+        """Branch-and-bound search for the most probable state (tnac4o.py:381-551).  Returns the energies.
+        ``shards`` (a :class:`tnac4o_b200.parallel.BranchShards`) spreads the branch batch of this one search over the
+        ranks of a process group; every rank returns the same result as the single-GPU call."""
+        if shards is not None and shards.world == 1:
+            shards = None
         dev = self._dev()
         c = Context.get(dev)
         t0 = time.time()
@@ -497,20 +553,23 @@ class tnac4o:
         self.logger.info('Preprocesing ... ')
         self._setup_rhoT(graduate_truncation=graduate_truncation, Dmax=Dmax, tolS=tolS, tolV=tolV, max_sweeps=max_sweeps)
         torch.cuda.current_stream(dev).synchronize()
+        if shards is not None:
+            self._replicate_rhoT(shards)
+            torch.cuda.current_stream(dev).synchronize()
         t_rho = time.time() - t0
         self.logger.info('Elapsed: %.2f seconds', t_rho)
         t0 = time.time()
         self.logger.info('Searching ... ')
-        if self.native_search:
+        if self.native_search and shards is None:
             self._native_search(M, relative_P_cutoff, min_dEng, t_rho, t0)
             self.logger.info('Elapsed search total: %.2f seconds', self.stats['seconds_rhoT'] + self.stats['seconds_search'])
             return self.energy
-        ws = self._alloc_search(M, int(np.max(self.N)), self._max_bond())
+        ws = self._alloc_search(M, int(np.max(self.N)), self._max_bond(), shards)
         for ny in range(self.Ny):
             keep_time = time.time()
             self.logger.info('Row %d / %d', ny + 1, self.Ny)
             br = ws['cur']
-            RRat = self._setup_RR(br, ny)
+            RRat = self._setup_RR(br, ny, shards)
             br.RL[:br.n] = 1.0
             for nx in range(self.Nx):
                 self._site_marginals(ws, ws['cur'], RRat, ny, nx)
@@ -584,13 +643,15 @@ class tnac4o:
     # ------------------------------------------------------------------ low-energy spectrum (droplets)
     def search_low_energy_spectrum(self, excitations_encoding=1, M=2 ** 10, relative_P_cutoff=1e-6, max_dEng=0.,
                                    lim_hd=0, min_dEng=1e-12, graduate_truncation=True, Dmax=32, tolS=1e-16,
-                                   tolV=1e-10, max_sweeps=20):
+                                   tolV=1e-10, max_sweeps=20, shards=None):
         """Ground state plus the hierarchy of droplets recorded while merging (tnac4o.py:652-915).
         ``excitations_encoding=1`` (snake-order independence) is implemented; 2 and 3 are listed as next rows
         in SURVEY.md section 8(f)."""
         if excitations_encoding != 1:
             raise NotImplementedError('Available droplets handling strategy on the GPU path is excitations_encoding = 1.')
         self.excitations_encoding = excitations_encoding
+        if shards is not None and shards.world == 1:
+            shards = None
         dev = self._dev()
         c = Context.get(dev)
         t0 = time.time()
@@ -598,9 +659,12 @@ class tnac4o:
         self.logger.info('Preprocesing ... ')
         self._setup_rhoT(graduate_truncation=graduate_truncation, Dmax=Dmax, tolS=tolS, tolV=tolV, max_sweeps=max_sweeps)
         torch.cuda.current_stream(dev).synchronize()
+        if shards is not None:
+            self._replicate_rhoT(shards)
+            torch.cuda.current_stream(dev).synchronize()
         t_rho = time.time() - t0
         t0 = time.time()
-        ws = self._alloc_search(M, int(np.max(self.N)), self._max_bond())
+        ws = self._alloc_search(M, int(np.max(self.N)), self._max_bond(), shards)
         ws['want_groups'] = True
         ws['gmin'] = torch.ones(1, dtype=F64, device=dev)
         self._exc_initialise()
@@ -608,7 +672,7 @@ class tnac4o:
         self.logger.info('Searching ... ')
         for ny in range(self.Ny):
             self.logger.info('Layer %d / %d', ny + 1, self.Ny)
-            RRat = self._setup_RR(ws['cur'], ny)
+            RRat = self._setup_RR(ws['cur'], ny, shards)
             ws['cur'].RL[:ws['cur'].n] = 1.0
             for nx in range(self.Nx):
                 self._site_marginals(ws, ws['cur'], RRat, ny, nx)

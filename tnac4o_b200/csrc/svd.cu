@@ -195,7 +195,8 @@ constexpr int CJ_MAXOWN = CJ_MAXPAIRS / CLJ;
 
 __global__ void __launch_bounds__(JT, 1)
 jacobi_cluster_kernel(double* __restrict__ E, int ldw, int a, int ext, int nc, int max_sweeps, double tol,
-                      const SvdMeta* __restrict__ meta, int* __restrict__ status /* [0] = sweeps, [1] = converged */) {
+                      const SvdMeta* __restrict__ meta, int* __restrict__ status /* [0] = sweeps, [1] = converged */,
+                      int vglob /* 1: the accumulated right vectors stay in global memory (L2), only the w-parts are resident */) {
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int ncl = (int)cluster.num_blocks();        // 8 or 16 (launch attribute)
@@ -205,15 +206,17 @@ jacobi_cluster_kernel(double* __restrict__ E, int ldw, int a, int ext, int nc, i
     __shared__ unsigned int cnt[2][CLJ_MAX];
     __shared__ unsigned int myrot;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int aw = (a + ncl - 1) / ncl, ej = (ext + ncl - 1) / ncl, ll = aw + ej;
+    const int aw = (a + ncl - 1) / ncl, ej = (ext + ncl - 1) / ncl, ll = vglob ? aw : aw + ej;
+    const int lls = ll | 1;                                       // odd row stride: pair rows fall on different banks
     const int wlo = rank * aw, jlo = rank * ej;
+    const int ejv = max(0, min(ej, ext - jlo));                   // my valid part of the j-slice (vglob path)
     const double floor2 = DEAD_FLOOR * DEAD_FLOOR * meta->fro2;
     for (int64_t i = tid; i < (int64_t)nc * ll; i += JT) {
         int k = (int)(i / ll), e = (int)(i % ll);
         double v = 0.0;
         if (e < aw) { if (wlo + e < a) v = E[(int64_t)k * ldw + wlo + e]; }
         else { int f = e - aw; if (jlo + f < ext) v = E[(int64_t)k * ldw + a + jlo + f]; }
-        Sl[i] = v;
+        Sl[(int64_t)k * lls + e] = v;
     }
     if (tid == 0) myrot = 0;
     cluster.sync();      // all CTAs started (required before the first distributed-shared-memory access)
@@ -234,8 +237,8 @@ jacobi_cluster_kernel(double* __restrict__ E, int ldw, int a, int ext, int nc, i
                     valid = (p < nc) && (q < nc);
                 }
                 if (valid) {
-                    const double* xp = Sl + (int64_t)p * ll;
-                    const double* xq = Sl + (int64_t)q * ll;
+                    const double* xp = Sl + (int64_t)p * lls;
+                    const double* xq = Sl + (int64_t)q * lls;
                     for (int e = sub; e < aw; e += 8) {
                         double u = xp[e], v = xq[e];
                         app += u * u; aqq += v * v; apq += u * v;
@@ -282,12 +285,41 @@ jacobi_cluster_kernel(double* __restrict__ E, int ldw, int a, int ext, int nc, i
                 if (sn == 0.0) continue;
                 int p = (r + i) % r1;
                 int q = (i == 0) ? r1 : (r + r1 - i) % r1;
-                double* xp = Sl + (int64_t)p * ll;
-                double* xq = Sl + (int64_t)q * ll;
-                for (int e = sub; e < ll; e += 8) {
-                    double u = xp[e], v = xq[e];
-                    xp[e] = cs * u - sn * v;
-                    xq[e] = sn * u + cs * v;
+                double* xp = Sl + (int64_t)p * lls;
+                double* xq = Sl + (int64_t)q * lls;
+                if (!vglob) {
+                    for (int e = sub; e < ll; e += 8) {
+                        double u = xp[e], v = xq[e];
+                        xp[e] = cs * u - sn * v;
+                        xq[e] = sn * u + cs * v;
+                    }
+                } else {
+                    // my slice of the right-vector parts lives in global memory (L2): no other CTA touches it, and the
+                    // block barrier below orders it for the warp that rotates these vectors next round.  The loads
+                    // of a chunk are issued before the shared-memory rotation so that the L2 round trip overlaps it.
+                    double* gp = E + (int64_t)p * ldw + a + jlo;
+                    double* gq = E + (int64_t)q * ldw + a + jlo;
+                    double gu[4], gv[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int e = sub + 8 * k;
+                        if (e < ejv) { gu[k] = gp[e]; gv[k] = gq[e]; }
+                    }
+                    for (int e = sub; e < ll; e += 8) {
+                        double u = xp[e], v = xq[e];
+                        xp[e] = cs * u - sn * v;
+                        xq[e] = sn * u + cs * v;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int e = sub + 8 * k;
+                        if (e < ejv) { gp[e] = cs * gu[k] - sn * gv[k]; gq[e] = sn * gu[k] + cs * gv[k]; }
+                    }
+                    for (int e = sub + 32; e < ejv; e += 8) {          // slices longer than 32 (not reached for k <= 512)
+                        double u = gp[e], v = gq[e];
+                        gp[e] = cs * u - sn * v;
+                        gq[e] = sn * u + cs * v;
+                    }
                 }
             }
             __syncthreads();
@@ -309,8 +341,9 @@ jacobi_cluster_kernel(double* __restrict__ E, int ldw, int a, int ext, int nc, i
     if (r1 < 1) converged = 1;
     for (int64_t i = tid; i < (int64_t)nc * ll; i += JT) {
         int k = (int)(i / ll), e = (int)(i % ll);
-        if (e < aw) { if (wlo + e < a) E[(int64_t)k * ldw + wlo + e] = Sl[i]; }
-        else { int f = e - aw; if (jlo + f < ext) E[(int64_t)k * ldw + a + jlo + f] = Sl[i]; }
+        const double x = Sl[(int64_t)k * lls + e];
+        if (e < aw) { if (wlo + e < a) E[(int64_t)k * ldw + wlo + e] = x; }
+        else { int f = e - aw; if (jlo + f < ext) E[(int64_t)k * ldw + a + jlo + f] = x; }
     }
     if (rank == 0 && tid == 0) { status[0] = sweep; status[1] = converged; }
 }
@@ -446,7 +479,7 @@ extern "C" int tn_svd(tn_ctx* ctx, void* stream, int m, int n, const double* C, 
     // small problems: everything resident in one CTA or one cluster without deflation -> no host read-back
     const size_t CL_SMEM = 210 * 1024;
     auto cluster_fits = [&](int nvec, int e, int ncl = CLJ) {
-        size_t ll = (size_t)ceil_div(a, ncl) + (size_t)ceil_div(e, ncl);
+        size_t ll = ((size_t)ceil_div(a, ncl) + (size_t)ceil_div(e, ncl)) | 1;
         return nvec >= 2 && nvec <= 2 * CJ_MAXPAIRS && (size_t)nvec * ll * sizeof(double) <= CL_SMEM;
     };
     const int ext_full = want_vectors ? kfull : 0;
@@ -508,12 +541,14 @@ extern "C" int tn_svd(tn_ctx* ctx, void* stream, int m, int n, const double* C, 
             TN_LAUNCHED(ctx);
         }
         sweeps = 1;
-    } else if (cluster_fits(nc, ext) || (wide_clusters() && wide_launchable() && cluster_fits(nc, ext, CLJ_MAX))) {
-        // cluster-resident: one launch, no host read-back inside the iteration.  8 CTAs when the live vectors fit,
-        // 16 (non-portable cluster size) for the larger problems that would otherwise take the multi-launch path
-        const int ncl = (cluster_fits(nc, ext) && !(wide_clusters() == 2 && wide_launchable() && nc >= 96 && cluster_fits(nc, ext, CLJ_MAX)))
-                            ? CLJ : CLJ_MAX;
-        size_t ll = (size_t)ceil_div(a, ncl) + (size_t)ceil_div(ext, ncl);
+    } else if (cluster_fits(nc, ext) || (wide_clusters() && wide_launchable() && cluster_fits(nc, 0, CLJ_MAX))) {
+        // cluster-resident: one launch, no host read-back inside the iteration.  8 CTAs when the live vectors fit;
+        // 16 CTAs (non-portable cluster size) for larger problems; and when even that is too small for vectors plus
+        // accumulated right vectors, 16 CTAs with only the w-parts resident and the right vectors rotated in L2
+        const bool fits8 = cluster_fits(nc, ext), fits16 = wide_clusters() && wide_launchable() && cluster_fits(nc, ext, CLJ_MAX);
+        const int ncl = (fits8 && !(wide_clusters() == 2 && fits16 && nc >= 96)) ? CLJ : CLJ_MAX;
+        const int vglob = (ncl == CLJ_MAX && !fits16) ? 1 : 0;
+        size_t ll = ((size_t)ceil_div(a, ncl) + (vglob ? 0 : (size_t)ceil_div(ext, ncl))) | 1;
         size_t smem = (size_t)nc * ll * sizeof(double);
         TN_CUDA(cudaFuncSetAttribute(jacobi_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CL_SMEM));
         TN_CUDA(cudaFuncSetAttribute(jacobi_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -529,7 +564,8 @@ extern "C" int tn_svd(tn_ctx* ctx, void* stream, int m, int n, const double* C, 
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        TN_CUDA(cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel, E, ldw, a, ext, nc, (int)MAX_SWEEPS, tol, (const SvdMeta*)meta, status));
+        TN_CUDA(cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel, E, ldw, a, ext, nc, (int)MAX_SWEEPS, tol, (const SvdMeta*)meta, status,
+                                   vglob));
         TN_LAUNCHED(ctx);
         sweeps = -1;
         if (!small) {

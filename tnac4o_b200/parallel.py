@@ -44,13 +44,28 @@ def sum_over_ranks(values, device=None):
 
 
 def gather_samples(energy, states):
-    """concatenate per-rank Gibbs samples in rank order (every rank receives the full arrays)"""
+    """concatenate per-rank Gibbs samples in rank order (every rank receives the full arrays); the data travel as
+    tensors (NCCL: device buffers), cell states as int32"""
     rank, world = world_info()
     if world == 1:
         return energy, states
-    parts = [None] * world
-    dist.all_gather_object(parts, (np.asarray(energy), np.asarray(states)))
-    return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts], axis=0)
+    energy, states = np.asarray(energy, dtype=np.float64), np.asarray(states)
+    nccl = dist.get_backend() == 'nccl'
+    dev = torch.device('cuda', torch.cuda.current_device()) if nccl else torch.device('cpu')
+    counts = [None] * world
+    dist.all_gather_object(counts, int(len(energy)))
+    cap = max(counts)
+    e = torch.zeros(cap, dtype=torch.float64, device=dev)
+    e[:len(energy)] = torch.from_numpy(energy).to(dev)
+    st = torch.zeros((cap, states.shape[1]), dtype=torch.int32, device=dev)
+    st[:len(energy)] = torch.from_numpy(states.astype(np.int32)).to(dev)
+    E = torch.empty((world * cap,), dtype=torch.float64, device=dev)
+    S = torch.empty((world * cap, states.shape[1]), dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(E, e)
+    dist.all_gather_into_tensor(S, st)
+    E, S = E.cpu().numpy(), S.cpu().numpy()
+    keep = np.concatenate([np.arange(r * cap, r * cap + c) for r, c in enumerate(counts)])
+    return E[keep], S[keep].astype(states.dtype)
 
 
 _SIGN = -2 ** 63

@@ -51,7 +51,7 @@ wrap(ops, 'truncation_rank', lambda a, k: 'truncation_rank')
 wrap(ops, 'diff_norm', lambda a, k: 'diff_norm')
 
 Nx, Ny = SHAPES[L]
-ins = tnac4o_b200.tnac4o(mode='Ising', Nx=Nx, Ny=Ny, Nc=8, J=droplet_couplings(L), beta=3)
+ins = tnac4o_b200.tnac4o(mode='Ising', Nx=Nx, Ny=Ny, Nc=8, J=droplet_couplings(L), beta=float(os.environ.get('TN_PROFILE_BETA', '3')))
 ins.native_rows = False          # same kernel sequence as the native row driver, but every primitive call is visible here
 ins.search_ground_state(M=M, relative_P_cutoff=1e-8, Dmax=D)       # warm-up (not instrumented meaningfully)
 log.clear()

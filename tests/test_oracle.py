@@ -103,3 +103,21 @@ def test_compress_keeps_the_state():
     ov = psi.compress(Dmax=64, tolS=1e-16, tolV=1e-10, max_sweeps=4)
     assert abs(ov - 1.0) < 1e-10
     assert max(psi.discarded) < 1e-12
+
+
+def test_full_size_fixtures_are_consistent_with_the_couplings():
+    """configs 4 and 5 at L=2048 (fixtures from the unmodified reference, too slow to regenerate in the CPU suite):
+    the stored states reproduce the stored energies under the oracle's energy_Jij restatement, the M=2^12 search finds
+    the same ground state as M=2^10 and as the groundstates_otn2d.txt line, and the Gibbs samples are at beta=1 energies"""
+    J = droplet_couplings(2048)
+    z4, z4b, z5 = golden('ref_l2048_m4096.npz'), golden('ref_l2048.npz'), golden('ref_gibbs_l2048.npz')
+    assert list(z4['params']) == [2048, 32, 4096] and list(z5['params']) == [2048, 32, 256]
+    e_file, bits_file = droplet_golden(2048, 1)
+    assert abs(float(z4['gs_energy'][0]) - e_file) < 1e-5 and float(z4['gs_energy'][0]) == float(z4b['gs_energy'][0])
+    assert int(z4['gs_degeneracy']) == 2
+    assert abs(energy_ising_sparse(J, z4['gs_bits'])[0] - float(z4['gs_energy'][0])) < 1e-6
+    assert int(z4['marginals']) > 3 * int(z4b['marginals'])                 # four times the branches, saturated
+    assert np.max(np.abs(z5['energy_Jij'] - z5['energy'])) < 1e-6           # examples/test_examples.py:56
+    # samples -> spins (1 - bit of the cell state, tnac4o.py:279-285) -> the same energies
+    bits = 1 - ((z5['states'][:, :, None].astype(np.int64) >> np.arange(8)) & 1)
+    assert np.max(np.abs(energy_ising_sparse(J, bits.reshape(256, 2048)) - z5['energy'])) < 1e-6

@@ -545,6 +545,8 @@ class tnac4o:
         ranks of a process group; every rank returns the same result as the single-GPU call."""
         if shards is not None and shards.world == 1:
             shards = None
+        if shards is not None:
+            shards.bytes_gathered = 0
         dev = self._dev()
         c = Context.get(dev)
         t0 = time.time()

@@ -38,5 +38,23 @@ elif what == 'search':
     ins = tnac4o_b200.tnac4o(mode='Ising', Nx=8, Ny=8, Nc=8, J=droplet_couplings(512), beta=3)
     ins.search_ground_state(M=1024, relative_P_cutoff=1e-8, Dmax=16)
     print(ins.energy, ins.stats)
+elif what == 'gibbs':
+    # the branch-parallel kernels at config-5 size: right environments (grouped DMMA GEMM) and marginals for 10^5 samples.
+    # The boundary MPS is built first; ncu --profile-from-start off captures only what follows cudaProfilerStart.
+    from conftest import droplet_couplings
+    import tnac4o_b200
+    ins = tnac4o_b200.tnac4o(mode='Ising', Nx=16, Ny=16, Nc=8, J=droplet_couplings(2048), beta=3)
+    ins._setup_rhoT(Dmax=32)
+    built = ins._setup_rhoT
+    ins._setup_rhoT = lambda **kw: None
+    np.random.seed(1)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    ins.Ny = 1                                  # one lattice row is enough for the capture
+    ins.order = np.arange(16)
+    ins.gibbs_sampling(M=100000, Dmax=32)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+    print(ins.stats)
 torch.cuda.synchronize()
 print('done', what)

@@ -1,0 +1,31 @@
+#!/usr/bin/env python
+"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list by kernel: launches, total time, share.
+    python tools/summarise_launches.py gpurun_out/launches.csv "comment line" > profiles/<name>_summary.csv"""
+import csv
+import re
+import sys
+from collections import defaultdict
+
+rows = []
+with open(sys.argv[1], newline='') as f:
+    lines = [l for l in f if not l.startswith('==')]
+rd = csv.reader(lines)
+hdr = next(rd)
+ik, iv, iu = hdr.index('Kernel Name'), hdr.index('Metric Value'), hdr.index('Metric Unit')
+agg = defaultdict(list)
+for r in rd:
+    if len(r) <= iv:
+        continue
+    name = re.sub(r'^void ', '', r[ik])
+    name = re.sub(r'\(.*$', '', name).replace('<unnamed>::', '').replace('(anonymous namespace)::', '')
+    v = float(r[iv].replace(',', ''))
+    v *= {'ns': 1e-3, 'us': 1.0, 'usecond': 1.0, 'ms': 1e3, 'msecond': 1e3, 'nsecond': 1e-3}.get(r[iu], 1.0)
+    agg[name].append(v)
+tot = sum(sum(v) for v in agg.values())
+n = sum(len(v) for v in agg.values())
+print('# %s; %d launches' % (sys.argv[2] if len(sys.argv) > 2 else sys.argv[1], n))
+print('# per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes')
+print('kernel,launches,sum_us,share_pct,median_us,max_us')
+for name, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+    v = sorted(v)
+    print('"%s",%d,%.1f,%.2f,%.2f,%.2f' % (name, len(v), sum(v), 100 * sum(v) / tot, v[len(v) // 2], v[-1]))

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Row-by-row comparison of the boundary-MPS build, GPU path vs numpy oracle (run on the GPU box):
    sweeps and Schmidt-spectrum changes of every variational_compress call, bond dimensions, fidelity of rhoT[ny].
-   python tools/diag_rows.py [L] [Dmax]"""
+   python tests/tools/diag_rows.py [L] [Dmax]"""
 import os
 import sys
 import warnings
@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 warnings.filterwarnings('ignore')
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 from conftest import SHAPES, droplet_couplings  # noqa: E402

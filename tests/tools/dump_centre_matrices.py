@@ -1,8 +1,9 @@
 """Dump the 512 x 512 centre matrices the oracle hands to its SVD while compressing a 4-row slab of L=2048 instance 001
-(build container only; output under /tmp/svdsim).  usage: python tools/prototypes/dump_centre_matrices.py <beta>"""
+(build container only; output under /tmp/svdsim).  usage: python tests/tools/dump_centre_matrices.py <beta>"""
 import os, sys, numpy as np, warnings
 warnings.filterwarnings('ignore')
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 os.environ['OPENBLAS_NUM_THREADS'] = '1'
 import bench
 import oracle.mps_ref as mr

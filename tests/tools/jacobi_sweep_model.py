@@ -1,8 +1,8 @@
 """numpy model of the cluster Jacobi kernel (csrc/svd.cu: same orientation rule, dead-vector floor, round-robin tournament and
 rotation threshold) used to count sweeps on the real 512 x 512 centre matrices of an L=2048 boundary-MPS build.
 
-    python tools/prototypes/dump_centre_matrices.py 3        # oracle run, writes /tmp/svdsim/C_beta3.npz (build container only)
-    python tools/prototypes/jacobi_sweep_model.py /tmp/svdsim/C_beta3.npz 8
+    python tests/tools/dump_centre_matrices.py 3        # oracle run, writes /tmp/svdsim/C_beta3.npz (build container only)
+    python tests/tools/jacobi_sweep_model.py /tmp/svdsim/C_beta3.npz 8
 
 Measured (droplet instance 001, Dmax=32): beta=3: 100-234 live vectors, 11-14 sweeps, initial ordering by norm changes
 nothing; beta=1: 512 live vectors, 10-12 sweeps.  Test / design infrastructure only -- the product never imports it."""

@@ -460,14 +460,106 @@ class RefSolver:
             dpos, dstate = self.d[k]
             self.invd.setdefault((dpos[0], dstate[0], dpos[-1], dstate[-1]), []).append(k)
 
+    # ------------------------------------------------------------------ droplets (encodings 2 and 3: adjacency graph)
+    def _adj_setup(self, J, Nx, Ny, ind):
+        """adjacency of the coupling graph and, per cell, the spins behind every XOR pattern (tnac4o.py:2020-2036)."""
+        off = scipy.sparse.triu(J, 1) != 0
+        self.adj = (off + off.T).toarray()
+        self.xor2ind = []
+        for ny in range(Ny):
+            for nx in range(Nx):
+                spins = np.asarray(ind[ny][nx])
+                flipped = cell_bits(len(spins)).astype(bool)          # row x: which spins of the cell pattern x flips
+                self.xor2ind.append([spins[flipped[x]] for x in range(2 ** len(spins))])
+
+    def _shape_of(self, e):
+        return self.d[e] if isinstance(e, (int, np.integer)) else e
+
+    def _spins_of(self, shape):
+        """tnac4o.py:2081-2085 (negative int8 patterns index the table from its end, i.e. as unsigned bytes)."""
+        return np.hstack([self.xor2ind[pos][pat] for pos, pat in zip(*shape)])
+
+    def _is_connected(self, shape):
+        """tnac4o.py:2087-2104."""
+        spins = self._spins_of(shape)
+        reached, left = spins[:1], spins[1:]
+        while reached.size > 0 and left.size > 0:
+            hit = np.any(self.adj[reached, :][:, left], axis=0)
+            reached, left = left[hit], left[~hit]
+        return left.size == 0
+
+    def _touching(self, e1, e2):
+        """tnac4o.py:2122-2134."""
+        a, b = self._spins_of(self._shape_of(e1)), self._spins_of(self._shape_of(e2))
+        return np.any(self.adj[a, :][:, b])
+
+    def _hd_between(self, e1, e2):
+        """tnac4o.py:2157-2187 (bit counts through bin() of the signed pattern, as the reference does)."""
+        (p1, s1), (p2, s2) = self._shape_of(e1), self._shape_of(e2)
+        i = j = hd = 0
+        while i < len(p1) and j < len(p2):
+            if p1[i] == p2[j]:
+                hd += bin(np.bitwise_xor(s1[i], s2[j])).count('1')
+                i, j = i + 1, j + 1
+            elif p1[i] < p2[j]:
+                hd += bin(s1[i]).count('1')
+                i += 1
+            else:
+                hd += bin(s2[j]).count('1')
+                j += 1
+        for k in range(i, len(p1)):
+            hd += bin(s1[k]).count('1')
+        for k in range(j, len(p2)):
+            hd += bin(s2[k]).count('1')
+        return hd
+
+    def _merge_shapes(self, e1, e2):
+        """XOR of two droplets on the union of their cells, cancelled cells removed (tnac4o.py:2206-2247)."""
+        (p1, s1), (p2, s2) = self._shape_of(e1), self._shape_of(e2)
+        pos = np.union1d(p1, p2)
+        pat = np.zeros(len(pos), dtype=np.int64)
+        pat[np.searchsorted(pos, p1)] = s1
+        pat[np.searchsorted(pos, p2)] = np.bitwise_xor(pat[np.searchsorted(pos, p2)], np.asarray(s2, dtype=np.int64))
+        keep = pat != 0
+        return pos[keep].astype(np.int64), pat[keep]
+
+    def _enumerate_adj(self, excs, max_dEng=0., max_states=np.inf, one_layer=False):
+        """tnac4o.py:2337-2377: breadth-wise expansion, one popped excitation per state and pass."""
+        Eng, todo, flip = [0.0], [list(excs)], [[]]
+        progressed = True
+        while progressed:
+            progressed = False
+            k = 0
+            while k < len(Eng):
+                if todo[k]:
+                    exc = todo[k].pop()
+                    if Eng[k] + exc[0][0] <= max_dEng:
+                        Eng.append(Eng[k] + exc[0][0])
+                        flip.append(flip[k] + [exc[0][1]])
+                        rest = [x for x in todo[k] if not self._touching(x[0][1], exc[0][1])]
+                        todo.append(rest)
+                        if not one_layer:
+                            rest.extend(list(exc[1]))
+                        progressed = True
+                k += 1
+            if len(Eng) > max_states:
+                sel = np.array(Eng).argpartition(max_states)[:max_states]
+                Eng = [Eng[i] for i in sel]
+                flip = [flip[i] for i in sel]
+                todo = [todo[i] for i in sel]
+        return np.array(Eng), flip
+
     def search_low_energy_spectrum(self, excitations_encoding=1, M=2 ** 10, relative_P_cutoff=1e-6,
                                    max_dEng=0., lim_hd=0, min_dEng=1e-12, graduate_truncation=True,
                                    Dmax=32, tolS=1e-16, tolV=1e-10, max_sweeps=20):
-        """encoding 1 only: tnac4o.py:652-725, 727-915."""
-        if excitations_encoding != 1:
-            raise NotImplementedError('oracle covers excitations_encoding=1 (SURVEY.md section 8f-4)')
-        self.excitations_encoding = 1
+        """tnac4o.py:652-725 and the three variants 727-915 (encoding 1), 943-1133 (2), 1135-1358 (3); the search loop is
+        common, the encodings differ in what is recorded when branches merge."""
+        if excitations_encoding not in (1, 2, 3):
+            raise NotImplementedError('Available droplets handling strategies are excitations_encoding = 1, 2, 3.')
+        enc = self.excitations_encoding = excitations_encoding
         self._setup_rhoT(graduate_truncation, Dmax, tolS, tolV, max_sweeps)
+        if enc > 1:
+            self._adj_setup(self.J, self.Nx, self.Ny, self.ind)
         Nx = self.Nx
         vind = np.zeros((1, Nx + 1), dtype=self.indtype)
         states = np.zeros((1, Nx * self.Ny), dtype=self.indtype)
@@ -518,31 +610,76 @@ class RefSolver:
 
                 new_el = []
                 last = Nx * ny + nx
+                seen_w, seen_m = [], []           # what the device path hands to its droplet book (trace for the tests)
                 for g in keepg:
                     members = gorder[starts[g]:starts[g + 1]]
                     winner = rep[g]
                     bel = self.el[parent[winner]][:]
+                    fresh, recs = [], []
                     for m in members:
                         gap = Eng[m] - Engn[g]
                         if gap <= max_dEng and m != winner:
                             diff = np.bitwise_xor(states[winner], states[m])
                             dpos = diff.nonzero()[0]
                             dstate = diff[dpos]
-                            if lim_hd <= 1 or len(dstate) >= lim_hd:
-                                key = self._droplet_key(dpos, dstate)
-                                subs = [self._prune(se, max_dEng - (se[0][0] + gap))
-                                        for se in self.el[parent[m]]
-                                        if se[0][3] >= dpos[0] and se[0][0] + gap <= max_dEng]
-                                bel.append(((gap, key, dpos[0], last, prob[m] - probn[g]), tuple(subs)))
+                            recs.append((parent[m], gap, dpos, dstate))
+                            if enc == 1:
+                                if lim_hd <= 1 or len(dstate) >= lim_hd:
+                                    key = self._droplet_key(dpos, dstate)
+                                    subs = [self._prune(se, max_dEng - (se[0][0] + gap))
+                                            for se in self.el[parent[m]]
+                                            if se[0][3] >= dpos[0] and se[0][0] + gap <= max_dEng]
+                                    bel.append(((gap, key, dpos[0], last, prob[m] - probn[g]), tuple(subs)))
+                            elif enc == 2:
+                                # only connected differences become droplets; dependent sub-droplets follow (1071-1082)
+                                if (lim_hd <= 1 or len(dstate) >= lim_hd) and self._is_connected((dpos, dstate)):
+                                    key = self._droplet_key(dpos, dstate)
+                                    subs = [self._prune(se, max_dEng - (se[0][0] + gap)) for se in self.el[parent[m]]
+                                            if se[0][0] + gap <= max_dEng and self._touching(key, se[0][1])]
+                                    bel.append(((gap, key), tuple(subs)))
+                            else:
+                                # one layer: the difference combined with every independent set of the droplets of the
+                                # merged branch that touch it; connected combinations are stored flat (1259-1276)
+                                near = [se for se in self.el[parent[m]]
+                                        if se[0][0] + gap <= max_dEng and self._touching((dpos, dstate), se[0][1])]
+                                sE, sflip = self._enumerate_adj(near, max_dEng - gap, one_layer=True)
+                                for dE, keys in zip(sE, sflip):
+                                    shape = (dpos, dstate)
+                                    for k in keys:
+                                        shape = self._merge_shapes(shape, k)
+                                    if (lim_hd <= 1 or len(shape[1]) >= lim_hd) and self._is_connected(shape):
+                                        fresh.append(((dE + gap, self._droplet_key(*shape)), ()))
+                    if enc == 3:
+                        bel.extend(sorted(fresh, key=lambda x: x[0][0]))
                     new_el.append(bel)
+                    seen_w.append(parent[winner])
+                    seen_m.append(recs)
+                if self.trace:
+                    self.trace('droplets', ny=ny, nx=nx, winner_parent=seen_w, merged=seen_m)
                 vind, states = uniq[keepg], states[rep[keepg]]
                 prob, Eng, deg = probn[keepg], Engn[keepg], degn[keepg]
                 self.el = new_el
                 RLl = self._advance_left_env(RLl, vind, ny, nx)
-                self._collect_garbage()
+                if enc != 3:
+                    self._collect_garbage()
                 globalmin = min(globalmin, np.min(flag))
+            if enc == 3:
+                self._collect_garbage()
+                if self.trace:
+                    self.trace('row_end', ny=ny)
             vind[:, 1:] = vind[:, :-1]
             vind[:, 0] = 0
+        if enc == 3:
+            # greedy removal of near-duplicate droplets in energy order (tnac4o.py:1311-1326)
+            bel = sorted(self.el[0], key=lambda x: x[0][0])
+            if lim_hd > 1:
+                kept = []
+                for x in bel:
+                    if all(self._hd_between(x[0][1], y[0][1]) >= lim_hd for y in kept):
+                        kept.append(x)
+                bel = kept
+            self.el[0] = bel
+            self._collect_garbage()
         self.energy = Eng
         self.degeneracy = deg[0]
         self.states = states[:, self.order]
@@ -554,10 +691,15 @@ class RefSolver:
             dpos = self.order_i[dpos]
             srt = dpos.argsort()
             self.d[key] = (dpos[srt], dstate[srt])
+        if enc > 1:
+            self._adj_setup(self.J0, self.Nx_model, self.Ny_model, self.ind0)     # decode works in the model's orientation
         return Eng
 
     def _unpack(self, max_dEng, max_states):
-        """enumerate droplet combinations, snake-order independence (tnac4o.py:2295-2335)."""
+        """enumerate droplet combinations, snake-order independence (tnac4o.py:2295-2335); encodings 2 and 3 enumerate
+        through the adjacency graph (2287-2293)."""
+        if self.excitations_encoding > 1:
+            return self._enumerate_adj(self.el, max_dEng, max_states, one_layer=(self.excitations_encoding == 3))
         Eng, flip = [0.0], [[]]
         nsites = self.Nx_model * self.Ny_model
         stacks = [[((0, 0, -1, nsites - 1, 1), tuple(self.el))]]

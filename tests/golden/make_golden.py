@@ -16,6 +16,7 @@ Fixtures
   ref_l2048.npz       config 4 (M=2^10 variant): L=2048 #1, Dmax=32
   ref_l2048_m4096.npz config 4 as quoted: L=2048 #1, M=2^12, Dmax=32
   ref_gibbs_l2048.npz config 5 at M=256 samples: L=2048 #1, beta=1, seed 1
+  ref_encodings.npz   excitations_encoding = 2, 3 (adjacency-based droplets): L=128 spectra for several rotations / lim_hd, L=512
   ref_l1152.npz       config 3: L=1152 #1 spectrum (ee=1, dE=1) -> number of decoded states, energies
 """
 import os
@@ -181,6 +182,39 @@ def make_gibbs_l2048(M=256):
     np.savez_compressed(os.path.join(HERE, 'ref_gibbs_l2048.npz'), **out)
 
 
+def make_encodings():
+    """adjacency-based droplet encodings (excitations_encoding = 2, 3; examples/test_examples.py:59-104): decoded
+    spectra below dE = 1 for several rotations, a Hamming-distance limited run, and the sizes of the stored structures"""
+    out = {}
+    J = droplet_J(128, 1)
+    for ee, rot, hd in ((2, 0, 0), (2, 2, 0), (3, 0, 0), (3, 3, 0), (2, 0, 4), (3, 0, 4), (2, 1, 0), (3, 1, 0)):
+        ins = ref.tnac4o(mode='Ising', Nx=4, Ny=4, Nc=8, J=J, beta=3)
+        if rot:
+            ins.rotate_graph(rot)
+        ins.search_low_energy_spectrum(excitations_encoding=ee, M=1024, relative_P_cutoff=1e-8, Dmax=16, max_dEng=1.0, lim_hd=hd)
+        tag = 'ee%d_r%d_hd%d' % (ee, rot, hd)
+        out[tag + '_n_shapes'] = np.int64(len(ins.d))
+        out[tag + '_n_first_layer'] = np.int64(len(ins.el))
+        out[tag + '_first_layer_dE'] = np.array(sorted(e[0][0] for e in ins.el))
+        ins.decode_low_energy_states(max_dEng=1.0, max_states=2 ** 20)
+        order = np.lexsort(ins.states.T[::-1])
+        out[tag + '_energy'] = ins.energy[order]
+        out[tag + '_states'] = ins.states[order]
+        out[tag + '_energy_Jij'] = ref.energy_Jij(J, ins.binary_states())[order]
+    # a wider window on a larger lattice: L = 512, dE <= 0.5 (hundreds of states, several layers of the hierarchy)
+    J = droplet_J(512, 1)
+    for ee in (1, 2, 3):
+        ins = ref.tnac4o(mode='Ising', Nx=8, Ny=8, Nc=8, J=J, beta=3)
+        ins.search_low_energy_spectrum(excitations_encoding=ee, M=256, relative_P_cutoff=1e-8, Dmax=8, max_dEng=0.5)
+        tag = 'L512_ee%d' % ee
+        out[tag + '_n_shapes'] = np.int64(len(ins.d))
+        ins.decode_low_energy_states(max_dEng=0.5, max_states=2 ** 20)
+        order = np.lexsort(ins.states.T[::-1])
+        out[tag + '_energy'] = ins.energy[order]
+        out[tag + '_states'] = ins.states[order]
+    np.savez_compressed(os.path.join(HERE, 'ref_encodings.npz'), **out)
+
+
 def make_l1152():
     ins = ref.tnac4o(mode='Ising', Nx=12, Ny=12, Nc=8, J=droplet_J(1152, 1), beta=3)
     t0 = time.time()
@@ -217,6 +251,6 @@ if __name__ == '__main__':
          'l512': lambda: make_big(512, 16, 1024, 'ref_l512.npz'),
          'l2048': lambda: make_big(2048, 32, 1024, 'ref_l2048.npz'),
          'l2048m4096': lambda: make_big(2048, 32, 4096, 'ref_l2048_m4096.npz'),
-         'gibbs2048': make_gibbs_l2048,
+         'gibbs2048': make_gibbs_l2048, 'encodings': make_encodings,
          'l1152': make_l1152, 'j124': make_j124}[what]()
         print(what, 'done in %.1f s' % (time.time() - t0), flush=True)

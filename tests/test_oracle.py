@@ -121,3 +121,41 @@ def test_full_size_fixtures_are_consistent_with_the_couplings():
     # samples -> spins (1 - bit of the cell state, tnac4o.py:279-285) -> the same energies
     bits = 1 - ((z5['states'][:, :, None].astype(np.int64) >> np.arange(8)) & 1)
     assert np.max(np.abs(energy_ising_sparse(J, bits.reshape(256, 2048)) - z5['energy'])) < 1e-6
+
+
+ENCODING_CASES = [(2, 0, 0), (2, 2, 0), (3, 0, 0), (3, 3, 0), (2, 0, 4), (3, 0, 4), (2, 1, 0), (3, 1, 0)]
+
+
+@pytest.mark.parametrize('ee,rot,hd', ENCODING_CASES)
+def test_adjacency_encodings_match_reference_fixture(J128, ee, rot, hd):
+    """excitations_encoding = 2, 3 (tnac4o.py:943-1358; examples/test_examples.py:59-104 expects 31 states below dE = 1
+    for every encoding and rotation): stored structure sizes and the decoded spectrum, state by state"""
+    z = golden('ref_encodings.npz')
+    tag = 'ee%d_r%d_hd%d' % (ee, rot, hd)
+    ins = RefSolver(mode='Ising', Nx=4, Ny=4, Nc=8, J=J128, beta=3)
+    if rot:
+        ins.rotate_graph(rot)
+    ins.search_low_energy_spectrum(excitations_encoding=ee, M=1024, relative_P_cutoff=1e-8, Dmax=16, max_dEng=1.0, lim_hd=hd)
+    assert len(ins.d) == int(z[tag + '_n_shapes']) and len(ins.el) == int(z[tag + '_n_first_layer'])
+    np.testing.assert_allclose(sorted(e[0][0] for e in ins.el), z[tag + '_first_layer_dE'], atol=1e-10)
+    ins.decode_low_energy_states(max_dEng=1.0, max_states=2 ** 20)
+    if hd == 0:
+        assert len(ins.energy) == 31
+    order = np.lexsort(ins.states.T[::-1])
+    assert np.array_equal(ins.states[order], z[tag + '_states'])
+    np.testing.assert_allclose(ins.energy[order], z[tag + '_energy'], atol=1e-10)
+    assert np.max(np.abs(energy_ising_sparse(J128, ins.binary_states()) - ins.energy)) < 1e-4
+
+
+@pytest.mark.parametrize('ee', [2, 3])
+def test_adjacency_encodings_L512(ee):
+    """several layers of the droplet hierarchy: L = 512, dE <= 0.5 -> 302 states for every encoding"""
+    z = golden('ref_encodings.npz')
+    ins = RefSolver(mode='Ising', Nx=8, Ny=8, Nc=8, J=droplet_couplings(512), beta=3)
+    ins.search_low_energy_spectrum(excitations_encoding=ee, M=256, relative_P_cutoff=1e-8, Dmax=8, max_dEng=0.5)
+    assert len(ins.d) == int(z['L512_ee%d_n_shapes' % ee])
+    ins.decode_low_energy_states(max_dEng=0.5, max_states=2 ** 20)
+    order = np.lexsort(ins.states.T[::-1])
+    assert np.array_equal(ins.states[order], z['L512_ee%d_states' % ee])
+    assert np.array_equal(ins.states[order], z['L512_ee1_states'])           # the encodings agree on the spectrum
+    np.testing.assert_allclose(ins.energy[order], z['L512_ee%d_energy' % ee], atol=1e-10)

@@ -1,0 +1,53 @@
+"""GPU tests of excitations_encoding = 2 and 3 (adjacency-based droplets) through the public API.
+
+Status: the host-side structure (tnac4o_b200/droplets.py) is verified on the CPU against the reference fixtures
+(tests/test_droplets_host.py, driven by the oracle's merge records), and the device side re-uses the kernels and the
+record extraction of encoding 1 (tests/test_solver_gpu.py::test_spectrum_and_decode).  These end-to-end runs were
+written after the round's GPU budget was spent, so they are marked xfail(strict=False): a pass shows up as XPASS, a
+failure does not hide the results of the verified suite.  Remove the marks once they have been seen green on a B200."""
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import droplet_couplings, golden
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason='first device run pending (host logic verified on CPU; see module docstring)')]
+warnings.filterwarnings('ignore')
+
+
+@pytest.mark.parametrize('ee,rot,hd', [(2, 0, 0), (2, 2, 0), (3, 0, 0), (3, 3, 0), (2, 0, 4), (3, 0, 4)])
+def test_adjacency_encodings_end_to_end(J128, ee, rot, hd):
+    import tnac4o_b200
+    z = golden('ref_encodings.npz')
+    tag = 'ee%d_r%d_hd%d' % (ee, rot, hd)
+    ins = tnac4o_b200.tnac4o(mode='Ising', Nx=4, Ny=4, Nc=8, J=J128, beta=3)
+    if rot:
+        ins.rotate_graph(rot)
+    ins.search_low_energy_spectrum(excitations_encoding=ee, M=1024, relative_P_cutoff=1e-8, Dmax=16, max_dEng=1.0, lim_hd=hd)
+    assert len(ins.d) == int(z[tag + '_n_shapes']) and len(ins.el) == int(z[tag + '_n_first_layer'])
+    ins.decode_low_energy_states(max_dEng=1.0, max_states=2 ** 20)
+    if hd == 0:
+        assert len(ins.energy) == 31                                        # examples/test_examples.py:62
+    order = np.lexsort(ins.states.T[::-1])
+    assert np.array_equal(ins.states[order], z[tag + '_states'])
+    np.testing.assert_allclose(ins.energy[order], z[tag + '_energy'], atol=1e-10)
+    E = tnac4o_b200.energy_Jij(J128, ins.binary_states())
+    assert np.max(np.abs(E - ins.energy)) < 1e-4
+
+
+@pytest.mark.parametrize('ee', [2, 3])
+def test_adjacency_encodings_L512_and_file_round_trip(ee, tmp_path):
+    import os
+    import tnac4o_b200
+    z = golden('ref_encodings.npz')
+    ins = tnac4o_b200.tnac4o(mode='Ising', Nx=8, Ny=8, Nc=8, J=droplet_couplings(512), beta=3)
+    ins.search_low_energy_spectrum(excitations_encoding=ee, M=256, relative_P_cutoff=1e-8, Dmax=8, max_dEng=0.5)
+    fn = os.path.join(tmp_path, 'spectrum_ee%d.npy' % ee)
+    ins.save(fn)
+    back = tnac4o_b200.load(fn)                                              # e04: decode from the file
+    back.decode_low_energy_states(max_dEng=0.5, max_states=2 ** 20)
+    order = np.lexsort(back.states.T[::-1])
+    assert len(back.energy) == 302 and np.array_equal(back.states[order], z['L512_ee%d_states' % ee])
+    np.testing.assert_allclose(back.energy[order], z['L512_ee%d_energy' % ee], atol=1e-10)

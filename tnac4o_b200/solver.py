@@ -40,6 +40,8 @@ def load(file_name):
     if d.get('excitations_encoding') is not None:
         ins.excitations_encoding = d.get('excitations_encoding')
         ins.d, ins.invd, ins.el, ins.free_d = d.get('d'), d.get('invd'), d.get('el'), d.get('free_d')
+        if ins.excitations_encoding > 1:
+            ins.adj = d.get('adj')
     return ins
 
 
@@ -646,11 +648,11 @@ class tnac4o:
     def search_low_energy_spectrum(self, excitations_encoding=1, M=2 ** 10, relative_P_cutoff=1e-6, max_dEng=0.,
                                    lim_hd=0, min_dEng=1e-12, graduate_truncation=True, Dmax=32, tolS=1e-16,
                                    tolV=1e-10, max_sweeps=20, shards=None):
-        """Ground state plus the hierarchy of droplets recorded while merging (tnac4o.py:652-915).
-        ``excitations_encoding=1`` (snake-order independence) is implemented; 2 and 3 are listed as next rows
-        in SURVEY.md section 8(f)."""
-        if excitations_encoding != 1:
-            raise NotImplementedError('Available droplets handling strategy on the GPU path is excitations_encoding = 1.')
+        """Ground state plus the hierarchy of droplets recorded while merging (tnac4o.py:652-1358).
+        ``excitations_encoding=1``: independence from the snake order (727-915); ``2`` and ``3``: independence from the
+        adjacency of the coupling graph, hierarchical or one layer (943-1358; host structure in droplets.py)."""
+        if excitations_encoding not in (1, 2, 3):
+            raise NotImplementedError('Available droplets handling strategies are excitations_encoding = 1, 2, 3.')
         self.excitations_encoding = excitations_encoding
         if shards is not None and shards.world == 1:
             shards = None
@@ -670,6 +672,11 @@ class tnac4o:
         ws['want_groups'] = True
         ws['gmin'] = torch.ones(1, dtype=F64, device=dev)
         self._exc_initialise()
+        book = None
+        if excitations_encoding > 1:
+            from .droplets import AdjacencyDroplets
+            book = AdjacencyDroplets(excitations_encoding)
+            book.set_adjacency(self.J, [self.ind[ny][nx] for ny in range(self.Ny) for nx in range(self.Nx)])
         nsites = self.Nx * self.Ny
         self.logger.info('Searching ... ')
         for ny in range(self.Ny):
@@ -680,17 +687,71 @@ class tnac4o:
                 self._site_marginals(ws, ws['cur'], RRat, ny, nx)
                 old = ws['cur']
                 groups = self._site_step(ws, RRat, ny, nx, M, relative_P_cutoff, min_dEng)
-                self._record_droplets(ws, old, groups, ny * self.Nx + nx, nsites, max_dEng, lim_hd)
-                self._exc_clear_d()
+                if book is None:
+                    self._record_droplets(ws, old, groups, ny * self.Nx + nx, nsites, max_dEng, lim_hd)
+                    self._exc_clear_d()
+                else:
+                    book.site_update(*self._merged_branches(ws, old, groups, ny * self.Nx + nx, nsites, max_dEng),
+                                     max_dEng, lim_hd)
+                    book.end_of_site()
+            if book is not None:
+                book.end_of_row()
             br = ws['cur']
             check(lib.tn_row_shift(c.handle, c.stream, br.n, br.vind.stride(0), ptr(br.vind)))
         self._finish_search(ws, t_rho, t0)
+        if book is not None:
+            book.finish(self.order_i, lim_hd)
+            self.d, self.invd, self.el, self.free_d = book.d, book.invd, book.el, book.free_d
+            # decoding works in the model's orientation (tnac4o.py:1131, 1356)
+            book.set_adjacency(self.J0, [self.ind0[ny][nx] for ny in range(self.Ny_model) for nx in range(self.Nx_model)])
+            self.adj = book.adj
+            return self.energy
         self.el = self.el[0]
         for key, (dpos, dstate) in self.d.items():
             dpos = self.order_i[dpos]
             srt = dpos.argsort()
             self.d[key] = (dpos[srt], dstate[srt])
         return self.energy
+
+    def _merged_branches(self, ws, old, groups, last, nsites, max_dEng):
+        """What the adjacency encodings record at one site (tnac4o.py:1063-1075, 1251-1262): for every kept branch the
+        old branch of its winner, and for every branch merged into it within max_dEng (old branch, dE, dpos, dstate).
+        The XOR differences come from one tn_xor_diff launch, as for encoding 1."""
+        dev = self._dev()
+        c = Context.get(dev)
+        K, G = groups['K'], groups['G']
+        order = groups['order']
+        Bn = ws['cur'].n
+        host = lambda t, n: t[:n].cpu().numpy()
+        g_rep, g_start, g_size = host(ws['g_rep'], G), host(ws['g_start'], G), host(ws['g_size'], G)
+        g_E = host(ws['g_E'], G)
+        sel = host(ws['sel'], Bn)
+        Enew = host(ws['Enew'], K)
+        parent, cell = host(ws['parent'], K), host(ws['cell'], K)
+        pw, pm, pg = [], [], []
+        for j, g in enumerate(sel):
+            if g_size[g] > 1:
+                members = order[g_start[g]:g_start[g] + g_size[g]]
+                gap = Enew[members] - g_E[g]
+                for m in members[(gap <= max_dEng) & (members != g_rep[g])]:
+                    pw.append(g_rep[g]); pm.append(m); pg.append(j)
+        merged = [[] for _ in sel]
+        if pw:
+            npairs = len(pw)
+            i32 = lambda a: torch.as_tensor(np.asarray(a, dtype=np.int32), device=dev)
+            row_a, row_b = i32(parent[pw]), i32(parent[pm])
+            cell_a, cell_b = i32(cell[pw]), i32(cell[pm])
+            out_pos = torch.empty((npairs, nsites), dtype=torch.int16, device=dev)
+            out_xor = torch.empty((npairs, nsites), dtype=torch.uint8, device=dev)
+            out_len = torch.empty(npairs, dtype=torch.int32, device=dev)
+            check(lib.tn_xor_diff(c.handle, c.stream, npairs, nsites, last, ptr(old.states), ptr(row_a), ptr(cell_a),
+                                  ptr(row_b), ptr(cell_b), ptr(out_pos), ptr(out_xor), ptr(out_len)))
+            out_pos, out_xor, out_len = out_pos.cpu().numpy(), out_xor.cpu().numpy().view(np.int8), out_len.cpu().numpy()
+            for k in range(npairs):
+                m, g = pm[k], sel[pg[k]]
+                merged[pg[k]].append((int(parent[m]), Enew[m] - g_E[g], out_pos[k, :out_len[k]].astype(np.int64),
+                                      out_xor[k, :out_len[k]].copy()))
+        return [int(parent[g_rep[g]]) for g in sel], merged
 
     def _record_droplets(self, ws, old, groups, last, nsites, max_dEng, lim_hd):
         """excitation lists of the new branches (tnac4o.py:844-882).  The XOR differences between the winner and the
@@ -785,8 +846,19 @@ class tnac4o:
         for k in live:
             self.invd.setdefault(self._exc_get_sh(self.d[k]), []).append(k)
 
+    def _adjacency_book(self):
+        """droplet structure of encodings 2 / 3 around the solver's (or a loaded file's) d / el / adj"""
+        from .droplets import AdjacencyDroplets
+        book = AdjacencyDroplets(self.excitations_encoding)
+        book.set_adjacency(self.adj, [self.ind0[ny][nx] for ny in range(self.Ny_model) for nx in range(self.Nx_model)])
+        book.d, book.invd, book.el, book.free_d = self.d, self.invd, self.el, self.free_d
+        return book
+
     def _exc_unpack(self, max_dEng=0., max_states=np.inf):
-        """all droplet combinations below max_dEng, snake-order independence (tnac4o.py:2295-2335)"""
+        """all droplet combinations below max_dEng: snake-order independence (tnac4o.py:2295-2335) for encoding 1,
+        adjacency-based independence (2337-2377) for encodings 2 and 3"""
+        if getattr(self, 'excitations_encoding', 1) > 1:
+            return self._adjacency_book().unpack(max_dEng=max_dEng, max_states=max_states)
         Eng, flip = [0.0], [[]]
         nsites = self.Nx_model * self.Ny_model
         stacks = [[((0, 0, -1, nsites - 1, 1), tuple(self.el))]]
@@ -867,6 +939,8 @@ class tnac4o:
         if hasattr(self, 'excitations_encoding'):
             d.update({'excitations_encoding': self.excitations_encoding, 'd': self.d, 'invd': self.invd, 'el': self.el,
                       'free_d': self.free_d})
+            if self.excitations_encoding > 1:
+                d['adj'] = scipy.sparse.csr_matrix(self.adj)
         np.save(file_name, d)
 
     def show_properties(self):

@@ -67,3 +67,18 @@ def test_host_model_tables_match_oracle(J128=None):
             Wr, dr, rr = ref.site_weights(ny, nx)
             assert np.array_equal(Wc, Wr) and np.array_equal(dm, dr) and np.array_equal(rm, rr)
             assert np.array_equal(lat.traced(Wc, dm, rm, 2 ** lat.sd[ny][nx], 2 ** lat.sr[ny][nx]), ref.traced_mpo(ny, nx))
+
+
+def test_public_names_of_the_reference_package():
+    """tnac4o/__init__.py:1-2 of the reference: the names a user script imports"""
+    import numpy as np
+    import tnac4o_b200
+    for name in ('tnac4o', 'load', 'load_Jij', 'round_Jij', 'minus_Jij', 'Jij_f2p', 'energy_Jij', 'energy_RMF'):
+        assert hasattr(tnac4o_b200, name), name
+    # energy_RMF on the model of examples/e05_minimal_RMF.py (2 x 2 corner of it): one site table + one bond table
+    J = {'fun': {1: np.array([[0, 1, 1], [1, 0, 1], [1, 1, 0]]), 2: np.array([-1.5, 0, 1.5])},
+         'fac': {(0, 0, 0, 1): 1, (0, 0, 1, 0): 1, (0, 0): 2, (1, 1): 2}, 'N': np.zeros((2, 2), dtype=int) + 3, 'Nx': 2, 'Ny': 2}
+    states = np.array([[0, 0, 0, 0], [0, 1, 2, 2], [2, 2, 0, 1]])
+    assert np.allclose(tnac4o_b200.energy_RMF(J, states), [-3.0, 2.0, 2.5])
+    assert abs(tnac4o_b200.round_Jij([[0, 1, 0.33]], 1 / 75)[0][2] - 25 / 75) < 1e-15
+    assert tnac4o_b200.Jij_f2p([[1, 2, 0.5]]) == [[0, 1, 0.5]] and tnac4o_b200.minus_Jij([[0, 1, 0.5]]) == [[0, 1, -0.5]]

@@ -49,3 +49,19 @@ def energy_Jij(J, states, device=None):
     E = torch.empty(states.shape[0], dtype=torch.float64, device=device)
     check(lib.tn_energy_ising(c.handle, c.stream, states.shape[0], L, ptr(bits), JJ.nnz, ptr(ci), ptr(cj), ptr(cv), ptr(E)))
     return E.cpu().numpy()
+
+
+def energy_RMF(J, states):
+    """cost function of a random-Markov-field model for rows of cell states (auxx.py:110-134): ``J['fac']`` maps a site
+    (ny, nx) or a bond (ny1, nx1, ny2, nx2) to the index of its table in ``J['fun']``.  Host glue like the loaders (one
+    table look-up per factor); the solver itself implements ``mode='Ising'`` only."""
+    states = np.asarray(states)
+    E = np.zeros(len(states))
+    Nx = J['Nx']
+    for where, f in J['fac'].items():
+        table = np.asarray(J['fun'][f])
+        if len(where) == 2:
+            E += table[states[:, where[0] * Nx + where[1]]]
+        elif len(where) == 4:
+            E += table[states[:, where[0] * Nx + where[1]], states[:, where[2] * Nx + where[3]]]
+    return E

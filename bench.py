@@ -214,6 +214,10 @@ def run_gpu(args):
 
     from tnac4o_b200 import parallel
     B = args.batch
+    # one host thread per concurrent instance (it spins while it waits for its stream): never more threads than cores
+    cores = len(os.sched_getaffinity(0))
+    if world * (B + 1) > cores:
+        B = max(2, cores // world - 1)
     J = instance_couplings(rank * B)
     t_prep = time.time()
     inss = [tnac4o_b200.tnac4o(mode='Ising', Nx=CFG['Nx'], Ny=CFG['Ny'], Nc=CFG['Nc'], J=instance_couplings(rank * B + i),
@@ -356,7 +360,8 @@ def run_gpu(args):
            'ms_per_step': 1e3 * total / args.steps, 'higher_is_better': False, 'scaling': 'weak', 'vs_baseline': None,
            'dtype': 'f64', 'data': 'droplet instance 001 (rank 0) + synthetic couplings on the same chimera pattern (other ranks)',
            'config': {'workload': 'e01 ground-state search L=2048 (16x16x8 chimera), M=2^10, Dmax=32, beta=3, P_cutoff=1e-8, no preconditioning',
-                      'batch_per_gpu': B, 'concurrency': 'one host thread + one CUDA stream per instance',
+                      'batch_per_gpu': B, 'batch_requested': args.batch, 'host_cores': cores,
+                      'concurrency': 'one host thread + one CUDA stream per instance',
                       'l2': 'flushed between steps (256 MiB write)', 'parity_energy_matches_golden': parity_ok},
            'latency_seconds_single_instance': lat,
            'seconds_rhoT_per_instance_under_concurrency': float(np.mean([s['seconds_rhoT'] for s in stats])) / B,

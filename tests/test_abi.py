@@ -82,3 +82,29 @@ def test_public_names_of_the_reference_package():
     assert np.allclose(tnac4o_b200.energy_RMF(J, states), [-3.0, 2.0, 2.5])
     assert abs(tnac4o_b200.round_Jij([[0, 1, 0.33]], 1 / 75)[0][2] - 25 / 75) < 1e-15
     assert tnac4o_b200.Jij_f2p([[1, 2, 0.5]]) == [[0, 1, 0.5]] and tnac4o_b200.minus_Jij([[0, 1, 0.5]]) == [[0, 1, -0.5]]
+
+
+def test_rotate_graph_host_logic_matches_oracle():
+    """rotate_graph (tnac4o.py:290-340) is host logic: lattice maps, rotated couplings and the per-cell divisions of the
+    product equal the oracle's for every quarter turn, on a non-square lattice too"""
+    import numpy as np
+    import tnac4o_b200
+    from conftest import droplet_couplings
+    from oracle import RefSolver
+    J = droplet_couplings(128)
+    for shape in ((4, 4), (8, 2)):
+        for rot in (1, 2, 3, 5):
+            a = tnac4o_b200.tnac4o(mode='Ising', Nx=shape[0], Ny=shape[1], Nc=8, J=J, beta=3)
+            b = RefSolver(mode='Ising', Nx=shape[0], Ny=shape[1], Nc=8, J=J, beta=3)
+            a.rotate_graph(rot)
+            b.rotate_graph(rot)
+            assert (a.Nx, a.Ny, a.rotation) == (b.Nx, b.Ny, b.rotation)
+            assert np.array_equal(a.order, b.order) and np.array_equal(a.order_i, b.order_i)
+            assert (abs(a.J - b.J)).nnz == 0
+            for ny in range(a.Ny):
+                for nx in range(a.Nx):
+                    assert np.array_equal(a.ind[ny][nx], b.ind[ny][nx])
+                    assert np.array_equal(a.id[ny][nx], b.id[ny][nx]) and np.array_equal(a.ir[ny][nx], b.ir[ny][nx])
+            assert np.array_equal(a.sd, b.sd) and np.array_equal(a.sr, b.sr)
+            offs = a._key_offsets(a.Ny - 1, a.Nx - 1)                  # merge-key layout stays within 128 bits
+            assert len(offs) == a.Nx + 1 and int(offs[-1]) < 128

@@ -137,7 +137,9 @@ int tn_build_site_tables(tn_ctx* ctx, void* stream, int nS, int nl, int nd, int 
 
 /* Right environments of one row level for nb row-start branches (tnac4o.py:1776-1782):
  *   RRout[b][a][l] = sum_{p,b',r} A[a,p,b'] RRin[b][b'][r] Wtr[l,p,r,u_b] / nfactor,  u_b = up[b * up_stride].
- * A (Dl, nd, Dr); RRin (nb, Dr, nr); RRout (nb, Dl, nl). */
+ * A (Dl, nd, Dr); RRin (nb, Dr, nr); RRout (nb, Dl, nl).  Evaluated as AW_u = A.Wtr[..u] once per level, then one
+ * grouped DMMA GEMM over the branches bucketed by u_b (temporaries from the context's stream-ordered pool); a branch's
+ * result does not depend on which other branches are in the call. */
 int tn_rr_level(tn_ctx* ctx, void* stream, const tn_site* site, int nb, int Dl, int Dr, const double* A,
                 const double* RRin, const uint8_t* up, int up_stride, double* RRout);
 

@@ -17,6 +17,7 @@ Fixtures
   ref_l2048_m4096.npz config 4 as quoted: L=2048 #1, M=2^12, Dmax=32
   ref_gibbs_l2048.npz config 5 at M=256 samples: L=2048 #1, beta=1, seed 1
   ref_encodings.npz   excitations_encoding = 2, 3 (adjacency-based droplets): L=128 spectra for several rotations / lim_hd, L=512
+  ref_saved_spectrum_ee{1,2}.npy   files written by the reference's save() (pickled dict), read back by tnac4o_b200.load
   ref_l1152.npz       config 3: L=1152 #1 spectrum (ee=1, dE=1) -> number of decoded states, energies
 """
 import os
@@ -215,6 +216,16 @@ def make_encodings():
     np.savez_compressed(os.path.join(HERE, 'ref_encodings.npz'), **out)
 
 
+def make_saved_files():
+    """files written by the reference's own save() (what e03 -s leaves for e04): L=128 spectra for encodings 1 and 2"""
+    J = droplet_J(128, 1)
+    for ee in (1, 2):
+        ins = ref.tnac4o(mode='Ising', Nx=4, Ny=4, Nc=8, J=J, beta=3)
+        ins.rotate_graph(1)
+        ins.search_low_energy_spectrum(excitations_encoding=ee, M=1024, relative_P_cutoff=1e-8, Dmax=16, max_dEng=1.0)
+        ins.save(os.path.join(HERE, 'ref_saved_spectrum_ee%d.npy' % ee))
+
+
 def make_l1152():
     ins = ref.tnac4o(mode='Ising', Nx=12, Ny=12, Nc=8, J=droplet_J(1152, 1), beta=3)
     t0 = time.time()
@@ -251,6 +262,6 @@ if __name__ == '__main__':
          'l512': lambda: make_big(512, 16, 1024, 'ref_l512.npz'),
          'l2048': lambda: make_big(2048, 32, 1024, 'ref_l2048.npz'),
          'l2048m4096': lambda: make_big(2048, 32, 4096, 'ref_l2048_m4096.npz'),
-         'gibbs2048': make_gibbs_l2048, 'encodings': make_encodings,
+         'gibbs2048': make_gibbs_l2048, 'encodings': make_encodings, 'saved': make_saved_files,
          'l1152': make_l1152, 'j124': make_j124}[what]()
         print(what, 'done in %.1f s' % (time.time() - t0), flush=True)

@@ -18,6 +18,12 @@ import argparse
 import json
 import os
 
+# BLAS / OpenMP thread pools are sized when the libraries load: pin them BEFORE numpy is imported, here and (through the
+# inherited environment) in every spawned worker of the CPU legs.  One BLAS thread per process is the fastest setting
+# for this workload (L=512 takes 43.7 s with 1 thread, 78.8 s with 8); parallelism of the CPU
+# arm comes from independent single-thread workers, one per host core.
+for _v in ('OPENBLAS_NUM_THREADS', 'OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'NUMEXPR_NUM_THREADS'):
+    os.environ[_v] = '1'
 os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')     # one hardware queue per concurrent solver stream
 import subprocess
 import sys
@@ -437,11 +443,20 @@ def extrapolate(s):
     return rho + search, rho, search
 
 
+def blas_threads():
+    """effective BLAS thread count of this process (asserted to be 1 in the CPU legs)"""
+    try:
+        from threadpoolctl import threadpool_info
+        n = [int(p.get('num_threads', 1)) for p in threadpool_info() if p.get('user_api') in ('blas', 'openmp')]
+        return max(n) if n else 1
+    except Exception:
+        return None
+
+
 def cpu_sample(J):
-    os.environ.setdefault('OPENBLAS_NUM_THREADS', '1')
     s = _sample_once(J)
     total, rho, search = extrapolate(s)
-    return {'value': total, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+    return {'value': total, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'blas_threads': blas_threads(),
             'seconds_rhoT_est': rho, 'seconds_search_est': search,
             'branch_marginals_per_s': s['marginals_row'] / s['t_search_row'],
             'sample': 'numpy port of the reference (oracle/), 1 BLAS thread: boundary-MPS build of a 4-row slab of the 16 lattice rows '
@@ -450,8 +465,9 @@ def cpu_sample(J):
 
 
 def _worker(rank, q, warm=False):
-    os.environ['OPENBLAS_NUM_THREADS'] = '1'
-    os.environ['OMP_NUM_THREADS'] = '1'
+    # the thread pins at the top of this file were applied when the spawned child re-imported it (before numpy)
+    nthr = blas_threads()
+    assert nthr in (None, 1), 'BLAS thread pinning failed in the worker: %r threads' % nthr
     if warm:
         # untimed warm-up step: imports, page cache and BLAS initialisation on a small instance (L = 128)
         import warnings
@@ -461,7 +477,9 @@ def _worker(rank, q, warm=False):
         RefSolver(mode='Ising', Nx=4, Ny=4, Nc=8, J=droplet_couplings(128), beta=3).search_ground_state(M=64, Dmax=8)
         q.put(None)
         return
-    q.put(_sample_once(instance_couplings(rank), cols=REF_COLS))
+    r = _sample_once(instance_couplings(rank), cols=REF_COLS)
+    r['blas_threads'] = nthr
+    q.put(r)
 
 
 REF_COLS = None   # full lattice width: the share of edge sites (small bonds) is not linear in the number of columns
@@ -475,9 +493,8 @@ def run_reference(args):
     import psutil
     cores = len(os.sched_getaffinity(0))
     mem_gb = psutil.virtual_memory().available / 2 ** 30
-    # measured on the 16-core B200 host: 16 concurrent workers are only 2.9x faster than one (memory-bound), so half
-    # the cores carry the workers and the step stays short
-    workers = int(max(1, min(cores // 2 if cores > 1 else 1, mem_gb // 6, 32)))
+    # one single-thread worker per host core (BLAS threads pinned to 1 at the top of this file, asserted in the worker)
+    workers = int(max(1, min(cores, mem_gb // 4, 64)))
     ctx = mp.get_context('spawn')
 
     def step(warm=False):
@@ -502,6 +519,7 @@ def run_reference(args):
     value = per_instance / workers               # instances run concurrently, one per core
     marg = float(np.mean([r['marginals_row'] / r['t_search_row'] for r in results])) * workers
     cpu = {'value': value, 'unit': UNIT, 'cores': workers, 'kind': 'port',
+           'blas_threads_per_worker': sorted({r.get('blas_threads') for r in results}, key=str),
            'sample': 'numpy port of the reference (oracle/): %d concurrent single-thread workers (1 BLAS thread each is the '
                      'fastest setting, SURVEY.md section 6), each timing a 4-row slab of the 16 lattice rows of the boundary-MPS build '
                      '(steady-state interior row x13) and the first lattice row of the search (x16); value = extrapolated seconds per '

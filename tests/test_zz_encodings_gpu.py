@@ -1,10 +1,9 @@
 """GPU tests of excitations_encoding = 2 and 3 (adjacency-based droplets) through the public API.
 
-Status: the host-side structure (tnac4o_b200/droplets.py) is verified on the CPU against the reference fixtures
-(tests/test_droplets_host.py, driven by the oracle's merge records), and the device side re-uses the kernels and the
-record extraction of encoding 1 (tests/test_solver_gpu.py::test_spectrum_and_decode).  These end-to-end runs were
-written after the round's GPU budget was spent, so they are marked xfail(strict=False): a pass shows up as XPASS, a
-failure does not hide the results of the verified suite.  Remove the marks once they have been seen green on a B200."""
+The host-side structure (tnac4o_b200/droplets.py) is also verified on the CPU against the reference fixtures
+(tests/test_droplets_host.py, driven by the oracle's merge records); the device side re-uses the kernels and the record
+extraction of encoding 1.  First seen green on a B200 in GPUTEST_r01.json (8 XPASS); the xfail marks are gone, so a
+regression turns the suite red."""
 import warnings
 
 import numpy as np
@@ -12,8 +11,7 @@ import pytest
 
 from conftest import droplet_couplings, golden
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason='first device run pending (host logic verified on CPU; see module docstring)')]
+pytestmark = [pytest.mark.gpu]
 warnings.filterwarnings('ignore')
 
 

@@ -226,6 +226,23 @@ int tn_apply_droplets(tn_ctx* ctx, void* stream, int nstates, int nsites, const 
                       const int32_t* flip_key, const int32_t* drop_ptr, const int16_t* drop_pos, const uint8_t* drop_xor,
                       uint8_t* out);
 
+/* Enumeration of all droplet combinations of an excitation tree (excitations_encoding = 1) with excitation energy
+ * <= max_dEng, at most max_states (the lowest), sorted by energy -- replaces the Python loop _exc_unpack_v1
+ * (tnac4o.py:2295-2335) as a level-synchronous expansion over a flattened tree.  HOST arrays describe the tree: node 0
+ * is the root (dE 0, first -1, last nsites - 1); h_child_ptr (nnodes + 1) / h_child_idx list every node's children in
+ * the reference's order; h_key[k] indexes the droplet dictionary passed to tn_decode_fetch.  Synchronises (the number of
+ * combinations created per wave sizes the next launch); *h_count = number of combinations kept. */
+typedef struct tn_decode tn_decode;
+int tn_decode_enumerate(tn_ctx* ctx, void* stream, int nsites, int nnodes, const double* h_dE, const int32_t* h_key,
+                        const int32_t* h_first, const int32_t* h_last, const int32_t* h_child_ptr, const int32_t* h_child_idx,
+                        double max_dEng, int64_t max_states, tn_decode** out, int64_t* h_count);
+/* Energies (excitation energy of combination i, ascending) and states (ground XOR the droplets of combination i) of the
+ * first `count` combinations -- replaces the per-state loop of decode_low_energy_states (tnac4o.py:1377-1385).  Device
+ * pointers; droplet dictionary in CSR form (drop_ptr / drop_pos / drop_xor). */
+int tn_decode_fetch(tn_ctx* ctx, tn_decode* dec, int64_t count, const uint8_t* ground, const int32_t* drop_ptr,
+                    const int16_t* drop_pos, const uint8_t* drop_xor, double* E_out, uint8_t* states_out);
+int tn_decode_free(tn_decode* dec);
+
 /* E[k] = sum_{i<j} J_ij s_i s_j + sum_i J_ii s_i for 0/1 encoded states (L per row), couplings in coordinate form. */
 int tn_energy_ising(tn_ctx* ctx, void* stream, int nstates, int L, const int8_t* bits, int64_t nnz, const int32_t* ci,
                     const int32_t* cj, const double* cv, double* E);

@@ -19,6 +19,11 @@ Fixtures
   ref_encodings.npz   excitations_encoding = 2, 3 (adjacency-based droplets): L=128 spectra for several rotations / lim_hd, L=512
   ref_saved_spectrum_ee{1,2}.npy   files written by the reference's save() (pickled dict), read back by tnac4o_b200.load
   ref_l1152.npz       config 3: L=1152 #1 spectrum (ee=1, dE=1) -> number of decoded states, energies
+  ref_saved_spectrum_l1152.npy + ref_l1152_decoded.npz   config 3 as e03 -s / e04 run it: the reference's saved file and the
+                      decoded state set (sha256 of the sorted rows), all 545 966 energies, level counts
+  ref_j124_sweep.npz  examples/e06 on J124 C=8 instances 1-20: per rotation energy / degeneracy and the selected pair,
+                      with the couplings and the lines of results_*J124*.txt
+  ref_rmf.npz         examples/e05 (RMF toy 5x3): spectra for the three encodings (test_examples.py:107-136)
 """
 import os
 import sys
@@ -244,6 +249,96 @@ def make_l1152():
     np.savez_compressed(os.path.join(HERE, 'ref_l1152.npz'), **out)
 
 
+def make_l1152_saved():
+    """config 3 end to end as examples/e03 -s + e04 run it: search, save (the file is committed: 54 kB), load, decode;
+    the fixture pins the decoded state SET (sha256 of the lexicographically sorted rows) and the whole spectrum"""
+    import hashlib
+    ins = ref.tnac4o(mode='Ising', Nx=12, Ny=12, Nc=8, J=droplet_J(1152, 1), beta=3)
+    ins.search_low_energy_spectrum(excitations_encoding=1, M=1024, relative_P_cutoff=1e-8, Dmax=32, max_dEng=1.0)
+    fn = os.path.join(HERE, 'ref_saved_spectrum_l1152.npy')
+    ins.save(fn)
+    back = ref.load(fn)
+    t0 = time.time()
+    back.decode_low_energy_states(max_dEng=1.0, max_states=2 ** 20)
+    out = {'seconds_decode': np.float64(time.time() - t0), 'n_states': np.int64(len(back.energy))}
+    st = np.ascontiguousarray(back.states.astype(np.int8))
+    st = st[np.lexsort(st.T[::-1])]
+    out['states_sha256'] = np.frombuffer(hashlib.sha256(st.tobytes()).digest(), dtype=np.uint8)
+    out['energies_sorted'] = np.sort(back.energy)
+    vals, counts = np.unique(np.round((back.energy - back.energy.min()) * 75).astype(np.int64), return_counts=True)
+    out['level_75dE'], out['level_count'] = vals, counts
+    out['states_head'] = st[:64]
+    np.savez_compressed(os.path.join(HERE, 'ref_l1152_decoded.npz'), **out)
+
+
+def make_j124_sweep(n_inst=20):
+    """J124 C=8 instances 1..n_inst: coupling lists and the lines of results_C8_J124.txt (energy, degeneracy), the
+    known answers of examples/e06 (4 rotations, lowest energy, largest degeneracy among the rotations reaching it)"""
+    out = {}
+    res = np.loadtxt('%s/Chimera_J124/C=8_J124/results_C8_J124.txt' % INST, dtype=np.int64)
+    out['results'] = res[:n_inst]
+    for k in range(1, n_inst + 1):
+        raw = np.loadtxt('%s/Chimera_J124/C=8_J124/%03d.txt' % (INST, k))
+        out['J_%03d_i' % k] = raw[:, 0].astype(np.int16)
+        out['J_%03d_j' % k] = raw[:, 1].astype(np.int16)
+        out['J_%03d_v' % k] = raw[:, 2].astype(np.int8)
+        assert np.array_equal(out['J_%03d_v' % k], raw[:, 2])
+    np.savez_compressed(os.path.join(HERE, 'ref_j124_sweep.npz'), **out)
+
+
+def rmf_model():
+    """the toy model of examples/e05_minimal_RMF.py:31-52"""
+    Nx, Ny = 5, 3
+    N = np.zeros((3, 5), dtype=int) + 3
+    fun = {1: np.array([[0, 1, 1], [1, 0, 1], [1, 1, 0]]), 2: np.array([-1.5, 0, 1.5]), 3: np.array([1.25, 0, -1.25])}
+    fac = {}
+    for ny in range(Ny):
+        for nx in range(Nx - 1):
+            fac[(ny, nx, ny, nx + 1)] = 1
+    for ny in range(Ny - 1):
+        for nx in range(Nx):
+            fac[(ny, nx, ny + 1, nx)] = 1
+    for ny in range(Ny):
+        for nx in range(Nx):
+            fac[(ny, nx)] = 3 if ny == 1 else 2
+    return {'fun': fun, 'fac': fac, 'N': N, 'Nx': Nx, 'Ny': Ny}
+
+
+def make_rmf():
+    """examples/e05 / test_examples.py:107-136: RMF toy, dE = 3.1, the three encodings under different rotations, plus a
+    ground-state search and a Gibbs run; add_noise consumes the global RNG, seeded here and in the tests"""
+    out = {}
+    for ee, rot in ((1, 0), (1, 1), (2, 2), (3, 3)):
+        ins = ref.tnac4o(mode='RMF', Nx=5, Ny=3, J=rmf_model(), beta=4)
+        if rot:
+            ins.rotate_graph(rot=rot)
+        if ee > 1:
+            np.random.seed(7)
+            ins.add_noise(amplitude=1e-7)
+        ins.search_low_energy_spectrum(excitations_encoding=ee, M=1024, relative_P_cutoff=1e-12, Dmax=32, max_dEng=3.1, lim_hd=0)
+        tag = 'ee%d_r%d' % (ee, rot)
+        out[tag + '_gs_energy'], out[tag + '_gs_states'] = ins.energy.copy(), ins.states.copy()
+        out[tag + '_gs_probability'] = np.asarray(ins.probability)
+        out[tag + '_n_shapes'] = np.int64(len(ins.d))
+        ins.decode_low_energy_states(max_dEng=3.1, max_states=100)
+        out[tag + '_energy'], out[tag + '_states'] = ins.energy.copy(), ins.states.copy()
+        out[tag + '_energy_check'] = ref.energy_RMF(rmf_model(), ins.states)
+    for rot in (0, 1):
+        ins = ref.tnac4o(mode='RMF', Nx=5, Ny=3, J=rmf_model(), beta=4)
+        if rot:
+            ins.rotate_graph(rot=rot)
+        ins.search_ground_state(M=64, relative_P_cutoff=1e-12, Dmax=32)
+        tag = 'gs_r%d' % rot
+        out[tag + '_energy'], out[tag + '_states'] = ins.energy.copy(), ins.states.copy()
+        out[tag + '_probability'], out[tag + '_degeneracy'] = np.asarray(ins.probability), np.int64(ins.degeneracy)
+        out[tag + '_discarded'] = np.float64(ins.discarded_probability)
+    ins = ref.tnac4o(mode='RMF', Nx=5, Ny=3, J=rmf_model(), beta=1)
+    np.random.seed(3)
+    ins.gibbs_sampling(M=64, Dmax=32)
+    out['gibbs_energy'], out['gibbs_states'] = ins.energy.copy(), ins.states.copy()
+    np.savez_compressed(os.path.join(HERE, 'ref_rmf.npz'), **out)
+
+
 def make_j124():
     raw = np.loadtxt('%s/Chimera_J124/C=8_J124/001.txt' % INST)
     J = [[int(r[0]) - 1, int(r[1]) - 1, float(r[2])] for r in raw]
@@ -263,5 +358,6 @@ if __name__ == '__main__':
          'l2048': lambda: make_big(2048, 32, 1024, 'ref_l2048.npz'),
          'l2048m4096': lambda: make_big(2048, 32, 4096, 'ref_l2048_m4096.npz'),
          'gibbs2048': make_gibbs_l2048, 'encodings': make_encodings, 'saved': make_saved_files,
-         'l1152': make_l1152, 'j124': make_j124}[what]()
+         'l1152': make_l1152, 'l1152saved': make_l1152_saved, 'j124': make_j124, 'j124sweep': make_j124_sweep,
+         'rmf': make_rmf}[what]()
         print(what, 'done in %.1f s' % (time.time() - t0), flush=True)

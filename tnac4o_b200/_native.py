@@ -11,7 +11,8 @@ from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_int64, c_void_p
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libtnac4o_b200.so')
+# TNAC4O_B200_LIB selects another build of the same library (tools/microbench: the phase-timer build)
+LIB_PATH = os.environ.get('TNAC4O_B200_LIB') or os.path.join(_HERE, 'lib', 'libtnac4o_b200.so')
 
 if not os.path.exists(LIB_PATH):
     raise ImportError('tnac4o_b200: %s is missing -- build it with `python tnac4o_b200/build.py` '
@@ -67,6 +68,10 @@ _SIGS = {
     'tn_xor_diff': (c_int, [P, P, c_int, c_int, c_int, P, P, P, P, P, P, P, P]),
     'tn_apply_droplets': (c_int, [P, P, c_int, c_int, P, P, P, P, P, P, P]),
     'tn_energy_ising': (c_int, [P, P, c_int, c_int, P, c_int64, P, P, P, P]),
+    'tn_decode_enumerate': (c_int, [P, P, c_int, c_int, P, P, P, P, P, P, c_double, c_int64, POINTER(c_void_p),
+                                    POINTER(c_int64)]),
+    'tn_decode_fetch': (c_int, [P, P, c_int64, P, P, P, P, P, P]),
+    'tn_decode_free': (c_int, [P]),
 }
 EXPORTED = sorted(_SIGS)
 for _name, (_res, _args) in _SIGS.items():

@@ -36,6 +36,17 @@ constexpr int NB = 128;        // outer block width
 constexpr int RT = 256;        // threads per CTA of the register kernel
 constexpr int RPT = 4;         // rows per thread
 
+// Optional phase timers (tools/microbench builds with -DTN_PHASES): cycles spent in each phase of the column loop,
+// accumulated by thread 0 of CTA 0 into a global array read back by tn_debug_phases().
+#ifdef TN_PHASES
+__device__ long long g_phase[16];
+#define PH_DECL long long ph_t = clock64(), ph_n;
+#define PH(k) do { if (tid == 0 && rank == 0) { ph_n = clock64(); g_phase[k] += ph_n - ph_t; ph_t = ph_n; } } while (0)
+#else
+#define PH_DECL
+#define PH(k) do { } while (0)
+#endif
+
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(RT, 1)
 qr_panel_reg_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, double* __restrict__ Vall, int ldv,
                     double* __restrict__ Tout) {
@@ -71,6 +82,8 @@ qr_panel_reg_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, doub
     // the columns still to be updated are slots 1 .. 15-j and the finished reflectors are slots 16-j .. 15.  The loop
     // body is therefore the same code for every column (a fully unrolled version is 160 KB of SASS and runs out of
     // the instruction cache).
+    PH_DECL
+    PH(0);
 #pragma unroll 1
     for (int j = 0; j < jb; ++j) {
         const int buf = j & 1;
@@ -85,6 +98,7 @@ qr_panel_reg_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, doub
 #pragma unroll
             for (int c = 0; c < JB; ++c) v[c] += x * row[q][c];
         }
+        PH(1);
         // transposing butterfly: after the halving steps lane l holds the warp total of slot idx(l)
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -121,7 +135,9 @@ qr_panel_reg_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, doub
                 for (int c = 0; c < JB; ++c) stage[c] = row[q][c];     // stage the pivot row (owner CTA only)
             }
         }
+        PH(2);
         __syncthreads();
+        PH(3);
         if (tid < JB) {
             double s = 0.0;
 #pragma unroll
@@ -134,7 +150,9 @@ qr_panel_reg_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, doub
                 for (int r = 0; r < CL; ++r) *cluster.map_shared_rank(&prow[buf][tid], r) = pv;
             }
         }
+        PH(4);
         cluster.sync();
+        PH(5);
         // ---- reflector parameters, tau * v^T a_slot and column j of T: 16 lanes, redundant scalar work
         if (tid < JB) {
             double wc = 0.0, w0 = 0.0;
@@ -161,7 +179,9 @@ qr_panel_reg_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, doub
             if (tid < j) Ts[tid * JB + j] = -tau * s;
             if (tid == j) { Ts[j * JB + j] = tau; par[0] = beta; par[1] = tau; par[2] = scale; }
         }
+        PH(6);
         __syncthreads();
+        PH(7);
         const double beta = par[0], scale = par[2];
         const int last = JB - 1 - j;                 // slots 1 .. last are the columns still to be updated
         // ---- apply the reflector to my rows, then rotate the slots
@@ -184,6 +204,7 @@ qr_panel_reg_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, doub
             for (int c = 0; c < JB - 1; ++c) row[q][c] = row[q][c + 1];
             row[q][JB - 1] = t0;
         }
+        PH(8);
     }
     // ---- write R (upper triangle of the pivot rows) and the explicit V; slot s holds column (s + jb) mod 16
 #pragma unroll
@@ -201,6 +222,7 @@ qr_panel_reg_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, doub
     }
     __syncthreads();
     if (rank == 0 && tid < JB * JB) Tout[tid] = Ts[tid];
+    PH(9);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -615,3 +637,12 @@ extern "C" int tn_qr_pos(tn_ctx* ctx, void* stream, int m, int n, double* A, int
     if (maxabs_bits) TN_CUDA(cudaMemcpyAsync(maxabs_bits, bits, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
     return TN_OK;
 }
+
+#ifdef TN_PHASES
+extern "C" int tn_debug_phases(long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, g_phase, sizeof(long long) * 16);
+    if (reset) { long long z[16] = {0}; cudaMemcpyToSymbol(g_phase, z, sizeof(z)); }
+    return 0;
+}
+#endif

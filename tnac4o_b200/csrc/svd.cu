@@ -348,12 +348,162 @@ jacobi_cluster_kernel(double* __restrict__ E, int ldw, int a, int ext, int nc, i
     if (rank == 0 && tid == 0) { status[0] = sweep; status[1] = converged; }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Cluster-resident Jacobi, second generation: ONE cluster barrier per tournament round.
+// The vectors are split along their length over the ncl CTAs of the cluster exactly as above (ncl = 1, 2, 4, 8 or 16,
+// the smallest size whose shared memory holds the problem; ncl = 1 runs without any cluster traffic).  Per round every
+// CTA computes the partial 2x2 Gram of every pair on its slice and sends the triple to ALL CTAs (all-gather through
+// DSMEM, double-buffered by round parity); after the barrier every CTA sums the ncl partials in the same fixed order
+// and derives the rotation itself -- bit-identical decisions everywhere, so there is no owner, no broadcast, no
+// second barrier and no exchange of rotation counts.  Eight lanes work on a pair (four pairs per warp); the lanes
+// that computed a pair's partial Gram also rotate it, so the only block barrier of a round is the one that
+// publishes the rotated vectors to the warps that meet them next.
+constexpr int JT2 = 1024;
+constexpr int J2_SLOTS = JT2 / 8;                     // pairs processed concurrently by one CTA
+
+__global__ void __launch_bounds__(JT2, 1)
+jacobi_cluster2_kernel(double* __restrict__ E, int ldw, int a, int ext, int nc, int max_sweeps, double tol,
+                       const SvdMeta* __restrict__ meta, int* __restrict__ status /* [0] = sweeps, [1] = converged */) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int ncl = (int)cluster.num_blocks();
+    extern __shared__ __align__(16) double Sl[];      // [nc][lls] | part[2][ncl][half][3]
+    __shared__ unsigned int rotcnt;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int aw = (a + ncl - 1) / ncl, ej = (ext + ncl - 1) / ncl, ll = aw + ej;
+    const int lls = ll | 1;                                       // odd row stride: pair rows fall on different banks
+    const int wlo = rank * aw, jlo = rank * ej;
+    const int nce = nc + (nc & 1), r1 = nce - 1, half = nce / 2;
+    double* part = Sl + (size_t)nc * lls;
+    const double floor2 = DEAD_FLOOR * DEAD_FLOOR * meta->fro2;
+    const double tol2 = tol * tol;
+    for (int64_t i = tid; i < (int64_t)nc * ll; i += JT2) {
+        int k = (int)(i / ll), e = (int)(i % ll);
+        double v = 0.0;
+        if (e < aw) { if (wlo + e < a) v = E[(int64_t)k * ldw + wlo + e]; }
+        else { int f = e - aw; if (jlo + f < ext) v = E[(int64_t)k * ldw + a + jlo + f]; }
+        Sl[(int64_t)k * lls + e] = v;
+    }
+    if (tid == 0) rotcnt = 0;
+    // every CTA of the cluster must have started before anyone writes into its shared memory
+    if (ncl > 1) cluster.sync(); else __syncthreads();
+    const int sub = lane & 7, slot = warp * 4 + (lane >> 3);
+    int sweep = 0, converged = (r1 < 1), it = 0;
+    for (; sweep < max_sweeps && r1 >= 1; ++sweep) {
+        unsigned int my_rot = 0;
+        for (int r = 0; r < r1; ++r, ++it) {
+            double* pbuf = part + (size_t)(it & 1) * ncl * half * 3;
+            if (ncl > 1) {
+                // ---- (1) partial Gram triples on my w-slice, all-gathered
+                for (int i0 = 0; i0 < half; i0 += J2_SLOTS) {
+                    const int i = i0 + slot;
+                    bool valid = (i < half);
+                    int p = 0, q = 0;
+                    if (valid) {
+                        p = (r + i) % r1;
+                        q = (i == 0) ? r1 : (r + r1 - i) % r1;
+                        valid = (p < nc) && (q < nc);
+                    }
+                    double app = 0.0, aqq = 0.0, apq = 0.0;
+                    if (valid) {
+                        const double* xp = Sl + (int64_t)p * lls;
+                        const double* xq = Sl + (int64_t)q * lls;
+                        for (int e = sub; e < aw; e += 8) {
+                            const double u = xp[e], v = xq[e];
+                            app += u * u; aqq += v * v; apq += u * v;
+                        }
+                    }
+#pragma unroll
+                    for (int o = 4; o > 0; o >>= 1) {
+                        app += __shfl_xor_sync(0xffffffffu, app, o);
+                        aqq += __shfl_xor_sync(0xffffffffu, aqq, o);
+                        apq += __shfl_xor_sync(0xffffffffu, apq, o);
+                    }
+                    if (i < half) {
+                        for (int d = sub; d < ncl; d += 8) {
+                            double* dst = cluster.map_shared_rank(pbuf + ((size_t)rank * half + i) * 3, d);
+                            dst[0] = app; dst[1] = aqq; dst[2] = apq;
+                        }
+                    }
+                }
+                cluster.sync();
+            }
+            // ---- (2) every CTA sums the partials in the same order, decides the rotation and applies it to its slices
+            for (int i0 = 0; i0 < half; i0 += J2_SLOTS) {
+                const int i = i0 + slot;
+                bool valid = (i < half);
+                int p = 0, q = 0;
+                if (valid) {
+                    p = (r + i) % r1;
+                    q = (i == 0) ? r1 : (r + r1 - i) % r1;
+                    valid = (p < nc) && (q < nc);
+                }
+                double* xp = Sl + (int64_t)p * lls;
+                double* xq = Sl + (int64_t)q * lls;
+                double app = 0.0, aqq = 0.0, apq = 0.0;
+                if (ncl > 1) {
+                    if (valid) {
+                        for (int src = sub; src < ncl; src += 8) {       // ncl = 16: lane adds sources sub and sub + 8
+                            const double* t3 = pbuf + ((size_t)src * half + i) * 3;
+                            app += t3[0]; aqq += t3[1]; apq += t3[2];
+                        }
+                    }
+                } else if (valid) {
+                    for (int e = sub; e < aw; e += 8) {
+                        const double u = xp[e], v = xq[e];
+                        app += u * u; aqq += v * v; apq += u * v;
+                    }
+                }
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) {
+                    app += __shfl_xor_sync(0xffffffffu, app, o);
+                    aqq += __shfl_xor_sync(0xffffffffu, aqq, o);
+                    apq += __shfl_xor_sync(0xffffffffu, apq, o);
+                }
+                if (valid && app > floor2 && aqq > floor2 && apq * apq > tol2 * app * aqq) {
+                    const double zeta = (aqq - app) / (2.0 * apq);
+                    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    const double cs = rsqrt(1.0 + t * t), sn = cs * t;
+                    for (int e = sub; e < ll; e += 8) {
+                        const double u = xp[e], v = xq[e];
+                        xp[e] = cs * u - sn * v;
+                        xq[e] = sn * u + cs * v;
+                    }
+                    if (sub == 0) my_rot++;
+                }
+            }
+            __syncthreads();
+        }
+        // ---- end of sweep: every CTA took the same decisions, so the block-local count is the global one
+        if (my_rot) atomicAdd(&rotcnt, my_rot);
+        __syncthreads();
+        const unsigned int total = rotcnt;
+        __syncthreads();
+        if (tid == 0) rotcnt = 0;
+        if (total == 0) { converged = 1; ++sweep; break; }
+    }
+    __syncthreads();
+    for (int64_t i = tid; i < (int64_t)nc * ll; i += JT2) {
+        int k = (int)(i / ll), e = (int)(i % ll);
+        const double x = Sl[(int64_t)k * lls + e];
+        if (e < aw) { if (wlo + e < a) E[(int64_t)k * ldw + wlo + e] = x; }
+        else { int f = e - aw; if (jlo + f < ext) E[(int64_t)k * ldw + a + jlo + f] = x; }
+    }
+    if (rank == 0 && tid == 0) { status[0] = sweep; status[1] = converged; }
+    // no CTA may exit while another one can still write partials into its shared memory
+    if (ncl > 1) cluster.sync();
+}
+
 // norms -> S (sorted descending, dead vectors = exact zeros at the end), singular vectors with the sign rule of
 // mps.svd (mps.py:35-39).  U and Vt must be zero-filled by the caller.
 __global__ void __launch_bounds__(JT, 1)
 jacobi_finish_kernel(const double* __restrict__ E, int ldw, int a, int ext, int nc, int kfull, int has_dead,
                      const SvdMeta* __restrict__ meta, const int* __restrict__ live_idx, double* __restrict__ U, int ldu,
                      double* __restrict__ Sout, double* __restrict__ Vt, int ldvt, double* sv_tmp, int* rank_tmp) {
+    // Every CTA of the grid recomputes all norms and ranks (cheap, and it avoids a second launch); the CTAs write
+    // identical values to sv_tmp / rank_tmp / Sout and each one reads back only what it wrote itself.  The singular
+    // vectors -- the bulk of the output traffic -- are then split over the CTAs.
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int use_rows = meta->use_rows;
     for (int k = warp; k < nc; k += JW) {
@@ -377,7 +527,7 @@ jacobi_finish_kernel(const double* __restrict__ E, int ldw, int a, int ext, int 
     }
     __syncthreads();
     if (ext == 0) return;
-    for (int k = warp; k < nc; k += JW) {
+    for (int k = blockIdx.x * JW + warp; k < nc; k += gridDim.x * JW) {
         const double* w = E + (int64_t)k * ldw;
         const double* jv = w + a;
         const double sk = sv_tmp[k];
@@ -482,11 +632,24 @@ extern "C" int tn_svd(tn_ctx* ctx, void* stream, int m, int n, const double* C, 
         size_t ll = ((size_t)ceil_div(a, ncl) + (size_t)ceil_div(e, ncl)) | 1;
         return nvec >= 2 && nvec <= 2 * CJ_MAXPAIRS && (size_t)nvec * ll * sizeof(double) <= CL_SMEM;
     };
+    // second-generation kernel: smallest cluster (1, 2, 4, 8, 16 CTAs) whose shared memory holds nvec vectors + partials
+    static const bool v1_only = [] { const char* e = getenv("TN_SVD_V1"); return e && e[0] == '1'; }();
+    auto fit2 = [&](int nvec, int e) -> int {
+        if (nvec < 2 || v1_only) return 0;
+        const int halfp = (nvec + 1) / 2;
+        for (int ncl = 1; ncl <= CLJ_MAX; ncl *= 2) {
+            if (ncl == CLJ_MAX && !(wide_clusters() && wide_launchable())) break;
+            size_t ll = ((size_t)ceil_div(a, ncl) + (size_t)ceil_div(e, ncl)) | 1;
+            size_t bytes = (size_t)nvec * ll * sizeof(double) + (ncl > 1 ? (size_t)2 * ncl * halfp * 3 * sizeof(double) : 0);
+            if (bytes <= CL_SMEM) return ncl;
+        }
+        return 0;
+    };
     const int ext_full = want_vectors ? kfull : 0;
     const int ldw_full = a + ext_full;
     const bool tiny = kfull <= 32 && (size_t)kfull * ldw_full * sizeof(double) <= SMEM_LIMIT;
     // above 64 vectors the read-back for deflation pays for itself (graded factors have 3-5x fewer live vectors)
-    const bool small = tiny || (kfull <= 64 && cluster_fits(kfull, ext_full));
+    const bool small = tiny || (kfull <= 64 && (fit2(kfull, ext_full) > 0 || cluster_fits(kfull, ext_full)));
     svd_select_kernel<<<1, 256, 0, st>>>(norms2, m, n, force, small ? 0 : 1, meta, live_idx);
     TN_LAUNCHED(ctx);
     int nc = kfull;
@@ -541,6 +704,38 @@ extern "C" int tn_svd(tn_ctx* ctx, void* stream, int m, int n, const double* C, 
             TN_LAUNCHED(ctx);
         }
         sweeps = 1;
+    } else if (const int ncl2 = fit2(nc, ext)) {
+        // second-generation cluster kernel: one barrier per round, smallest cluster that holds the problem
+        const int halfp = (nc + 1) / 2;
+        size_t ll = ((size_t)ceil_div(a, ncl2) + (size_t)ceil_div(ext, ncl2)) | 1;
+        size_t smem = (size_t)nc * ll * sizeof(double) + (ncl2 > 1 ? (size_t)2 * ncl2 * halfp * 3 * sizeof(double) : 0);
+        TN_CUDA(cudaFuncSetAttribute(jacobi_cluster2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CL_SMEM));
+        if (ncl2 > CLJ) TN_CUDA(cudaFuncSetAttribute(jacobi_cluster2_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(ncl2, 1, 1);
+        cfg.blockDim = dim3(JT2, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = ncl2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        TN_CUDA(cudaLaunchKernelEx(&cfg, jacobi_cluster2_kernel, E, ldw, a, ext, nc, (int)MAX_SWEEPS, tol, (const SvdMeta*)meta, status));
+        TN_LAUNCHED(ctx);
+        sweeps = -1;
+        if (!small) {
+            int* hs = (int*)((char*)ctx->pinned + 320);
+            TN_CUDA(cudaMemcpyAsync(hs, status, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+            TN_CUDA(cudaStreamSynchronize(st));
+            sweeps = hs[0];
+            if (!hs[1]) {
+                tn_set_error("Jacobi SVD of a %d x %d matrix (%d live vectors) did not converge in %d sweeps", m, n, nc, sweeps);
+                return TN_ERR_NOCONV;
+            }
+        }
     } else if (cluster_fits(nc, ext) || (wide_clusters() && wide_launchable() && cluster_fits(nc, 0, CLJ_MAX))) {
         // cluster-resident: one launch, no host read-back inside the iteration.  8 CTAs when the live vectors fit;
         // 16 CTAs (non-portable cluster size) for larger problems; and when even that is too small for vectors plus
@@ -604,7 +799,11 @@ extern "C" int tn_svd(tn_ctx* ctx, void* stream, int m, int n, const double* C, 
             return TN_ERR_NOCONV;
         }
     }
-    jacobi_finish_kernel<<<1, JT, 0, st>>>(E, ldw, a, ext, nc, kfull, has_dead, meta, live_idx, U, ldu, S, Vt, ldvt, sv_tmp, rank_tmp);
+    {
+        int fin_blocks = ext ? ceil_div(nc, JW) : 1;
+        if (fin_blocks > 16) fin_blocks = 16;
+        jacobi_finish_kernel<<<fin_blocks, JT, 0, st>>>(E, ldw, a, ext, nc, kfull, has_dead, meta, live_idx, U, ldu, S, Vt, ldvt, sv_tmp, rank_tmp);
+    }
     TN_LAUNCHED(ctx);
     if (h_sweeps) *h_sweeps = sweeps;
     return TN_OK;

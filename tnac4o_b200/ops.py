@@ -72,8 +72,12 @@ def pow2_scale_(x, bits, log2_accum=None):
     return x
 
 
+last_svd_sweeps = 0
+
+
 def svd(C, want_vectors=True):
     """thin SVD of a contiguous 2-d tensor by Jacobi rotations -> (U, S, Vt) or S"""
+    global last_svd_sweeps
     assert C.dim() == 2 and C.stride(1) == 1
     m, n = C.shape
     k = min(m, n)
@@ -84,6 +88,7 @@ def svd(C, want_vectors=True):
     c = _ctx(C)
     check(lib.tn_svd(c.handle, c.stream, m, n, ptr(C), max(C.stride(0), 1), ptr(U), k, ptr(S), ptr(Vt), n,
                      int(want_vectors), ctypes.byref(sweeps)))
+    last_svd_sweeps = sweeps.value
     return (U, S, Vt) if want_vectors else S
 
 

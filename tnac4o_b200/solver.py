@@ -855,51 +855,93 @@ class tnac4o:
         return book
 
     def _exc_unpack(self, max_dEng=0., max_states=np.inf):
-        """all droplet combinations below max_dEng: snake-order independence (tnac4o.py:2295-2335) for encoding 1,
-        adjacency-based independence (2337-2377) for encodings 2 and 3"""
-        if getattr(self, 'excitations_encoding', 1) > 1:
-            return self._adjacency_book().unpack(max_dEng=max_dEng, max_states=max_states)
-        Eng, flip = [0.0], [[]]
-        nsites = self.Nx_model * self.Ny_model
-        stacks = [[((0, 0, -1, nsites - 1, 1), tuple(self.el))]]
-        for nn in range(nsites - 1, -1, -1):
-            k = 0
-            while k < len(Eng):
-                for ee in stacks[k][-1][1]:
-                    if ee[0][3] == nn and Eng[k] + ee[0][0] <= max_dEng:
-                        Eng.append(Eng[k] + ee[0][0])
-                        flip.append(flip[k] + [ee[0][1]])
-                        stacks.append(stacks[k] + [ee])
-                    elif ee[0][3] > nn:
-                        break
-                k += 1
-            if len(Eng) > max_states:
-                keep = np.array(Eng).argpartition(max_states)[:max_states]
-                Eng = [Eng[i] for i in keep]
-                flip = [flip[i] for i in keep]
-                stacks = [stacks[i] for i in keep]
-            for k in range(len(Eng)):
-                while stacks[k][-1][0][2] >= nn:
-                    stacks[k].pop()
-        return np.array(Eng), flip
+        """droplet combinations below max_dEng for the adjacency encodings 2 and 3 (tnac4o.py:2337-2377); encoding 1 is
+        enumerated on the device (_decode_device)"""
+        return self._adjacency_book().unpack(max_dEng=max_dEng, max_states=max_states)
 
-    def decode_low_energy_states(self, max_dEng=0., max_states=1024):
-        """Expand the droplet tree into states (tnac4o.py:1360-1389); the XOR of droplet shapes onto the ground
-        state is one integer kernel over all states (tn_apply_droplets)."""
-        dev = self._dev()
-        c = Context.get(dev)
-        Eng, flip = self._exc_unpack(max_dEng=max_dEng, max_states=max_states)
-        order = Eng.argsort()
-        Eng = Eng[order]
-        count = min(max_states, len(Eng))
-        nsites = self.Nx * self.Ny
+    def _flatten_tree(self, slot):
+        """nested excitation tuples -> flat node arrays for tn_decode_enumerate: node 0 is the root the reference puts
+        under every stack (tnac4o.py:2308: dE 0, first -1, last N - 1); children keep their order"""
+        nsites = self.Nx_model * self.Ny_model
+        dE, key, first, last, kids = [0.0], [0], [-1], [nsites - 1], [[]]
+        todo = [(0, self.el)]
+        while todo:
+            node, children = todo.pop()
+            for exc in children:
+                head = exc[0]
+                k = len(dE)
+                dE.append(float(head[0])); key.append(slot[head[1]]); first.append(int(head[2])); last.append(int(head[3]))
+                kids.append([])
+                kids[node].append(k)
+                todo.append((k, exc[1]))
+        child_ptr = np.zeros(len(dE) + 1, dtype=np.int32)
+        child_ptr[1:] = np.cumsum([len(c) for c in kids])
+        child_idx = np.array([c for cs in kids for c in cs], dtype=np.int32)
+        return (np.array(dE, dtype=np.float64), np.array(key, dtype=np.int32), np.array(first, dtype=np.int32),
+                np.array(last, dtype=np.int32), child_ptr, child_idx)
+
+    def _droplet_csr_host(self):
+        """dictionary of droplet shapes as CSR arrays (numpy) + key -> slot map"""
         keys = sorted(self.d)
         slot = {k: i for i, k in enumerate(keys)}
         drop_ptr = np.zeros(len(keys) + 1, dtype=np.int32)
         for i, k in enumerate(keys):
             drop_ptr[i + 1] = drop_ptr[i] + len(self.d[k][0])
-        drop_pos = np.concatenate([self.d[k][0] for k in keys]).astype(np.int16) if keys else np.zeros(0, np.int16)
-        drop_xor = np.concatenate([self.d[k][1] for k in keys]).astype(np.int8).view(np.uint8) if keys else np.zeros(0, np.uint8)
+        drop_pos = np.concatenate([self.d[k][0] for k in keys]).astype(np.int16) if keys else np.zeros(1, np.int16)
+        drop_xor = np.concatenate([self.d[k][1] for k in keys]).astype(np.int8).view(np.uint8) if keys else np.zeros(1, np.uint8)
+        return slot, drop_ptr, drop_pos, drop_xor
+
+    def _droplet_csr(self):
+        dev = self._dev()
+        slot, drop_ptr, drop_pos, drop_xor = self._droplet_csr_host()
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        return slot, up(drop_ptr), up(drop_pos), up(drop_xor)
+
+    def _decode_device(self, max_dEng, max_states):
+        """encoding 1: level-synchronous expansion of the flattened tree on the device (csrc/decode.cu) -> sorted
+        excitation energies and states"""
+        dev = self._dev()
+        c = Context.get(dev)
+        nsites = self.Nx_model * self.Ny_model
+        slot, drop_ptr, drop_pos, drop_xor = self._droplet_csr()
+        dE, key, first, last, child_ptr, child_idx = self._flatten_tree(slot)
+        hp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        handle, count = ctypes.c_void_p(), ctypes.c_int64(0)
+        cap = int(min(max_states, 2 ** 62))
+        check(lib.tn_decode_enumerate(c.handle, c.stream, nsites, len(dE), hp(dE), hp(key), hp(first), hp(last), hp(child_ptr),
+                                      hp(child_idx), float(max_dEng), cap, ctypes.byref(handle), ctypes.byref(count)))
+        try:
+            n = int(count.value)
+            ground = torch.from_numpy(np.ascontiguousarray(self.states[0]).view(np.uint8).copy()).to(dev)
+            Eng = torch.empty(n, dtype=F64, device=dev)
+            states = torch.empty((n, nsites), dtype=torch.uint8, device=dev)
+            check(lib.tn_decode_fetch(c.handle, handle, n, ptr(ground), ptr(drop_ptr), ptr(drop_pos), ptr(drop_xor), ptr(Eng),
+                                      ptr(states)))
+            torch.cuda.current_stream(dev).synchronize()
+        finally:
+            lib.tn_decode_free(handle)
+        return Eng, states
+
+    def decode_low_energy_states(self, max_dEng=0., max_states=1024):
+        """Expand the droplet tree into states (tnac4o.py:1360-1389).  Encoding 1: enumeration, top-max_states cut, energy
+        sort and the XOR of droplet shapes onto the ground state all run on the device (tn_decode_enumerate / _fetch);
+        encodings 2 and 3: host enumeration (droplets.py) + one XOR kernel over all states (tn_apply_droplets)."""
+        dev = self._dev()
+        c = Context.get(dev)
+        t0 = time.time()
+        if getattr(self, 'excitations_encoding', 1) == 1:
+            Eng, states = self._decode_device(max_dEng, max_states)
+            Eng = Eng.cpu().numpy()
+            self.energy = Eng + self.energy[0]
+            self.states = states.cpu().numpy().view(np.int8)
+            self.stats['seconds_decode'] = time.time() - t0
+            return Eng[0]
+        Eng, flip = self._exc_unpack(max_dEng=max_dEng, max_states=max_states)
+        order = Eng.argsort()
+        Eng = Eng[order]
+        count = min(max_states, len(Eng))
+        nsites = self.Nx * self.Ny
+        slot, drop_ptr, drop_pos, drop_xor = self._droplet_csr()
         flip_ptr = np.zeros(count + 1, dtype=np.int32)
         flat = []
         for i in range(count):
@@ -909,11 +951,12 @@ class tnac4o:
         up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
         ground = up(np.ascontiguousarray(self.states[0]).view(np.uint8))
         out = torch.empty((count, nsites), dtype=torch.uint8, device=dev)
-        t = [up(flip_ptr), up(np.asarray(flat, dtype=np.int32)), up(drop_ptr), up(drop_pos), up(drop_xor)]
-        check(lib.tn_apply_droplets(c.handle, c.stream, count, nsites, ptr(ground), ptr(t[0]), ptr(t[1]), ptr(t[2]),
-                                    ptr(t[3]), ptr(t[4]), ptr(out)))
+        t = [up(flip_ptr), up(np.asarray(flat if flat else [0], dtype=np.int32))]
+        check(lib.tn_apply_droplets(c.handle, c.stream, count, nsites, ptr(ground), ptr(t[0]), ptr(t[1]), ptr(drop_ptr),
+                                    ptr(drop_pos), ptr(drop_xor), ptr(out)))
         self.energy = Eng + self.energy[0]
         self.states = out.cpu().numpy().view(np.int8)
+        self.stats['seconds_decode'] = time.time() - t0
         return Eng[0]
 
     # ------------------------------------------------------------------ results / files

@@ -269,6 +269,55 @@ def test_config3_L1152_spectrum_and_decode():
     assert len(np.unique(ins.states, axis=0)) == len(ins.states)        # all decoded states are distinct
 
 
+def test_config3_decode_of_the_reference_file_gives_the_reference_state_set():
+    """examples/e04 on the file the reference's e03 -s wrote for config 3 (L=1152, dE=1): the device enumeration must return
+    exactly the reference's 545 966 states -- the SET (sha256 of the sorted rows) and every energy bit for bit -- and do it
+    at least 20x faster than the reference's 18.9 s Python loop (tnac4o.py:2295-2335)"""
+    import hashlib
+    import os
+    import time
+    import tnac4o_b200
+    from conftest import GOLDEN
+    z = golden('ref_l1152_decoded.npz')
+    ins = tnac4o_b200.load(os.path.join(GOLDEN, 'ref_saved_spectrum_l1152.npy'))
+    ins.decode_low_energy_states(max_dEng=1.0, max_states=2 ** 20)          # warm-up (allocations)
+    ins = tnac4o_b200.load(os.path.join(GOLDEN, 'ref_saved_spectrum_l1152.npy'))
+    t0 = time.time()
+    ins.decode_low_energy_states(max_dEng=1.0, max_states=2 ** 20)
+    seconds = time.time() - t0
+    assert len(ins.energy) == int(z['n_states']) == 545966
+    assert np.all(np.diff(ins.energy) >= 0)
+    assert np.array_equal(ins.energy, z['energies_sorted'])
+    st = np.ascontiguousarray(ins.states)
+    st = st[np.lexsort(st.T[::-1])]
+    assert np.array_equal(st[:64], z['states_head'])
+    assert np.array_equal(np.frombuffer(hashlib.sha256(st.tobytes()).digest(), dtype=np.uint8), z['states_sha256'])
+    assert seconds * 20 < float(z['seconds_decode']), seconds
+    # the top-K cut keeps the lowest energies (ties at the cut are arbitrary in the reference as well)
+    cut = tnac4o_b200.load(os.path.join(GOLDEN, 'ref_saved_spectrum_l1152.npy'))
+    cut.decode_low_energy_states(max_dEng=1.0, max_states=1000)
+    assert np.array_equal(cut.energy, z['energies_sorted'][:1000])
+
+
+def test_config3_save_load_decode_round_trip(tmp_path):
+    """e03 -s then e04 on this package's own file at config 3: search, save, load, decode = decode of the live object"""
+    import tnac4o_b200
+    J = droplet_couplings(1152)
+    ins = make(J, L=1152)
+    ins.search_low_energy_spectrum(excitations_encoding=1, M=1024, relative_P_cutoff=1e-8, Dmax=32, max_dEng=1.0)
+    fn = str(tmp_path / 'l1152.npy')
+    ins.save(fn)
+    back = tnac4o_b200.load(fn)
+    ins.decode_low_energy_states(max_dEng=1.0, max_states=2 ** 20)
+    back.decode_low_energy_states(max_dEng=1.0, max_states=2 ** 20)
+    assert np.array_equal(ins.energy, back.energy) and np.array_equal(ins.states, back.states)
+    z = golden('ref_l1152_decoded.npz')
+    n_ref = int(z['n_states'])
+    assert abs(len(back.energy) - n_ref) <= 0.001 * n_ref
+    head = min(len(back.energy), n_ref, 4096)
+    np.testing.assert_allclose(back.energy[:head], z['energies_sorted'][:head], rtol=0, atol=1e-9)
+
+
 def test_config5_gibbs_L2048_reduced():
     """BASELINE config 5 at reduced sample count: beta = 1, L = 2048; sampled energies equal energy_Jij of the states"""
     import tnac4o_b200

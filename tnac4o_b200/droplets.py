@@ -14,10 +14,12 @@ import scipy.sparse
 
 
 class AdjacencyDroplets:
-    def __init__(self, encoding):
+    def __init__(self, encoding, mode='Ising'):
         if encoding not in (2, 3):
             raise ValueError('AdjacencyDroplets handles excitations_encoding 2 and 3')
         self.encoding = encoding
+        self.mode = mode
+        self.grid_Nx = None
         self.d, self.invd, self.el, self.free_d = {}, {}, [[]], 0
         self.adj = None
         self.cell_spins = None
@@ -32,8 +34,21 @@ class AdjacencyDroplets:
         self.cell_spins = [np.asarray(c, dtype=np.int64) for c in cells]
         self._spin_cache = {}
 
+    def set_grid(self, Nx, Ny):
+        """mode='RMF': droplets live on the sites of an Ny x Nx nearest-neighbour grid (tnac4o.py:2038-2041)"""
+        self.grid_Nx, self.grid_Ny = Nx, Ny
+        self.adj = np.zeros((0, 0))
+
+    def _grid_distance(self, a, b):
+        """Manhattan distances between two sets of sites of the grid (tnac4o.py:2103-2109, 2136-2142)"""
+        a, b = np.asarray(a), np.asarray(b)
+        ax, ay, bx, by = a % self.grid_Nx, a // self.grid_Nx, b % self.grid_Nx, b // self.grid_Nx
+        return np.abs(ax[:, None] - bx[None, :]) + np.abs(ay[:, None] - by[None, :])
+
     def spins(self, dpos, dstate):
         """global indices of the spins a droplet flips: the set bits of every XOR pattern, cell by cell"""
+        if self.mode == 'RMF':
+            return np.asarray(dpos, dtype=np.int64)
         parts = []
         for cell, pattern in zip(dpos, dstate):
             key = (int(cell), int(pattern) & 0xFF)
@@ -53,18 +68,25 @@ class AdjacencyDroplets:
         todo = self.spins(dpos, dstate)
         front, rest = todo[:1], todo[1:]
         while front.size and rest.size:
-            touched = self.adj[np.ix_(front, rest)].any(axis=0)
+            if self.mode == 'RMF':
+                touched = (self._grid_distance(front, rest) == 1).any(axis=0)
+            else:
+                touched = self.adj[np.ix_(front, rest)].any(axis=0)
             front, rest = rest[touched], rest[~touched]
         return rest.size == 0
 
     def overlap(self, e1, e2):
         """does any spin of one droplet couple to a spin of the other? (tnac4o.py:2129-2134)"""
         a, b = self._shape(e1), self._shape(e2)
+        if self.mode == 'RMF':
+            return bool((self._grid_distance(a[0], b[0]) <= 1).any())
         return bool(self.adj[np.ix_(self.spins(*a), self.spins(*b))].any())
 
-    @staticmethod
-    def hamming(dstate):
-        """size of a droplet as the reference counts it in Ising mode: number of touched cells (tnac4o.py:2151-2152)"""
+    def hamming(self, dstate):
+        """size of a droplet as the reference counts it (tnac4o.py:2143-2150): touched cells in Ising mode, set bits of the
+        XOR patterns in RMF mode"""
+        if self.mode == 'RMF':
+            return sum(self._ones(v) for v in dstate)
         return len(dstate)
 
     @staticmethod
@@ -77,6 +99,10 @@ class AdjacencyDroplets:
         """number of spins in which two droplets differ, as the reference counts it (tnac4o.py:2170-2187)"""
         (p1, s1), (p2, s2) = self._shape(e1), self._shape(e2)
         n1, n2, hd = 0, 0, 0
+        if self.mode == 'RMF':          # sites on which the two patterns differ (tnac4o.py:2179-2195)
+            both = {int(p): int(v) for p, v in zip(p1, s1)}
+            other = {int(p): int(v) for p, v in zip(p2, s2)}
+            return sum(1 for p in set(both) | set(other) if both.get(p) != other.get(p))
         while n1 < len(p1) and n2 < len(p2):
             if p1[n1] == p2[n2]:
                 hd += self._ones(int(s1[n1]) ^ int(s2[n2]))

@@ -132,6 +132,74 @@ class IsingLattice:
         return W
 
 
+class RMFLattice:
+    """Random Markov Field on an Ny x Nx grid (mode='RMF', tnac4o.py:160-163, 1446-1456): one variable per site with N[ny][nx]
+    local states, factors ``J['fun'][J['fac'][key]]`` on sites (key = (ny, nx): vector) and on nearest-neighbour bonds
+    (key = (ny1, nx1, ny2, nx2): matrix indexed [state 1, state 2]).  Same interface as :class:`IsingLattice`; a bond index
+    IS the neighbouring state, so the bond maps are the identity (or 0 on legs without a factor)."""
+
+    def __init__(self, J, Nx, Ny, N):
+        self.Nx, self.Ny, self.Nc = Nx, Ny, 1
+        self.J = J
+        self.N = np.asarray(N, dtype=int).copy()
+        self.divide()
+
+    def divide(self):
+        Ny, Nx, fac = self.Ny, self.Nx, self.J['fac']
+        self.ll, self.lu, self.lr, self.ld = (np.ones((Ny, Nx), dtype=int) for _ in range(4))
+        for ny in range(Ny):
+            for nx in range(Nx):
+                if ((ny, nx - 1, ny, nx) in fac) or ((ny, nx, ny, nx - 1) in fac):
+                    self.ll[ny, nx] = self.N[ny][nx - 1]
+                if ((ny, nx, ny, nx + 1) in fac) or ((ny, nx + 1, ny, nx) in fac):
+                    self.lr[ny, nx] = self.N[ny][nx + 1]
+                if ((ny - 1, nx, ny, nx) in fac) or ((ny, nx, ny - 1, nx) in fac):
+                    self.lu[ny, nx] = self.N[ny - 1][nx]
+                if ((ny, nx, ny + 1, nx) in fac) or ((ny + 1, nx, ny, nx) in fac):
+                    self.ld[ny, nx] = self.N[ny + 1][nx]
+                for leg in (self.lr[ny, nx], self.ld[ny, nx]):
+                    # the reference's tensor only exists for legs of size 1 or N (tnac4o.py:1648-1665)
+                    if leg not in (1, self.N[ny][nx]):
+                        raise ValueError('RMF: neighbouring sites coupled by a factor must have the same number of states')
+        width = lambda a: np.ceil(np.log2(np.maximum(a, 1))).astype(int)       # bits of a bond index in the merge key
+        self.sl, self.su, self.sr, self.sd = width(self.ll), width(self.lu), width(self.lr), width(self.ld)
+        self.sN = width(self.N)
+        self.ind = [[np.array([ny * Nx + nx]) for nx in range(Nx)] for ny in range(Ny)]
+
+    def _bond(self, a, b, shape):
+        """factor between site a = (ny, nx) (row index) and its left / upper neighbour b (column index)"""
+        fac, fun = self.J['fac'], self.J['fun']
+        if b + a in fac:
+            return np.asarray(fun[fac[b + a]], dtype=float).T
+        if a + b in fac:
+            return np.asarray(fun[fac[a + b]], dtype=float)
+        return np.zeros(shape)
+
+    def energy_tables(self, ny, nx):
+        """Es[s], Esl[s, left state], Esu[s, upper state] (tnac4o.py:1532-1557)"""
+        N = int(self.N[ny][nx])
+        fac, fun = self.J['fac'], self.J['fun']
+        Es = np.asarray(fun[fac[(ny, nx)]], dtype=float).reshape(N) if (ny, nx) in fac else np.zeros(N)
+        Esl = self._bond((ny, nx), (ny, nx - 1), (N, int(self.ll[ny, nx]))) if nx > 0 else np.zeros((N, 1))
+        Esu = self._bond((ny, nx), (ny - 1, nx), (N, int(self.lu[ny, nx]))) if ny > 0 else np.zeros((N, 1))
+        return Es, Esl, Esu
+
+    def exponents(self, ny, nx, beta):
+        """beta (min - E) for the site, left-bond and up-bond factors, and the bond maps d(s), r(s) = s mod leg size
+        (tnac4o.py:1609-1638, 1477-1489)"""
+        N = int(self.N[ny][nx])
+        Es, E1, E4 = self.energy_tables(ny, nx)
+        if E1.shape[1] != self.ll[ny, nx]:
+            E1 = np.zeros((N, int(self.ll[ny, nx])))
+        if E4.shape[1] != self.lu[ny, nx]:
+            E4 = np.zeros((N, int(self.lu[ny, nx])))
+        E0 = beta * (np.min(Es) - Es)
+        E1 = beta * (np.min(E1) - E1)
+        E4 = beta * (np.min(E4) - E4)
+        s = np.arange(N)
+        return E0, E1, E4, np.mod(s, self.ld[ny, nx]), np.mod(s, self.lr[ny, nx])
+
+
 class HostTables:
     """Host half of the per-site constants: every small table of every site packed into ONE pinned float64 buffer and
     one uint8 buffer, so that the upload is two copies per instance (~34 MB at L = 2048)."""
@@ -147,7 +215,7 @@ class HostTables:
                 E0, E1, E4, dmap, rmap = lattice.exponents(ny, nx, beta)
                 Es, Esl, Esu = lattice.energy_tables(ny, nx)
                 nS, nl, nu = E0.shape[0], E1.shape[1], E4.shape[1]
-                nd, nr = int(2 ** lattice.sd[ny][nx]), int(2 ** lattice.sr[ny][nx])
+                nd, nr = int(lattice.ld[ny][nx]), int(lattice.lr[ny][nx])
                 parts = (E0, E1.reshape(nS, nl), E4.reshape(nS, nu), Xu[ny][nx][:nu], Xl[ny][nx][:nl], Xr[ny][nx][:nr],
                          Xd[ny][nx][:nd], Es, Esl.reshape(nS, nl), Esu.reshape(nS, nu))
                 meta = {'dims': (nS, nl, nd, nr, nu), 'off': {}, 'moff': moff}

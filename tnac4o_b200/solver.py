@@ -17,7 +17,7 @@ import torch
 
 from . import mps, ops
 from ._native import Context, check, lib, ptr
-from .model import HostTables, IsingLattice, cell_bits, upload_site_tables, upper_triangular
+from .model import HostTables, IsingLattice, RMFLattice, cell_bits, upload_site_tables, upper_triangular
 
 F64 = torch.float64
 _NEG_INF_BITS = 0x000FFFFFFFFFFFFF          # order-preserving encoding of -inf (common.cuh: ordered_bits)
@@ -47,11 +47,15 @@ def load(file_name):
 
 class tnac4o:
     r"""Tensor-network solver for Ising problems on a quasi-2d lattice (see the reference docstring,
-    tnac4o.py:78-143).  ``mode='Ising'``; spin index :math:`i = k N_x N_c + l N_c + m`."""
+    tnac4o.py:78-143).  ``mode='Ising'``: spin index :math:`i = k N_x N_c + l N_c + m`, ``J`` a list of ``[i, j, Jij]``;
+    ``mode='RMF'``: a Random Markov Field on the Ny x Nx grid, ``J = {'fun': ..., 'fac': ..., 'N': ..., 'Nx', 'Ny'}``
+    (tnac4o.py:104-118)."""
 
     def __init__(self, mode='Ising', Nx=4, Ny=4, Nc=8, beta=1, J=None, device=None):
-        if mode != 'Ising':
-            raise NotImplementedError("tnac4o_b200 implements mode='Ising' (RMF is outside the hot path, SURVEY.md section 2 row 24)")
+        if mode not in ('Ising', 'RMF'):
+            raise ValueError("mode is 'Ising' or 'RMF'")
+        if mode == 'RMF':
+            Nc = 1
         if Nc > 8:
             raise ValueError('Single cluster is too large (cell states are stored as one byte: Nc <= 8).')
         self.mode, self.beta = mode, beta
@@ -73,16 +77,29 @@ class tnac4o:
         self.native_rows = True      # boundary-MPS rows through the native driver (False: Python MPS methods)
         self.native_search = True    # branch-and-bound loop through the native driver (False: the Python loop below)
         self.build_rhoT0 = False     # the reference also contracts the last row (rhoT[0] / rhoB[Ny]), which nothing reads
-        if J is not None:
+        if J is not None and mode == 'Ising':
             self.J = upper_triangular(J, self.L)
             self.J0 = self.J.copy()
             self._divide_couplings()
             self.ind0 = [[self.lat.ind[ny][nx] for nx in range(Nx)] for ny in range(Ny)]
             self.active = int(sum(len(a) for row in self.ind0 for a in row))
+        elif J is not None:
+            self.J = J.copy()                       # tnac4o.py:192-197
+            self.Nrmf = np.asarray(J['N'], dtype=int).copy()
+            if int(np.max(self.Nrmf)) > 256:
+                raise ValueError('RMF: at most 256 states per site (states are stored as one byte)')
+            self.J0, self.ind0 = [], []
+            self._divide_couplings()
 
     # ------------------------------------------------------------------ model preparation (host)
     def _divide_couplings(self):
         """tnac4o.py:1391-1457"""
+        if self.mode == 'RMF':
+            self.lat = RMFLattice(self.J, self.Nx, self.Ny, self.Nrmf)
+            for name in ('ind', 'N', 'sN', 'sl', 'sd', 'sr', 'su', 'll', 'lu', 'lr', 'ld'):
+                setattr(self, name, getattr(self.lat, name))
+            self._reset_X()
+            return
         self.lat = IsingLattice(self.J, self.Nx, self.Ny, self.Nc)
         for name in ('ind', 'N', 'sN', 'sl', 'sd', 'sr', 'su', 'lr', 'ld', 'id', 'ir', 'Jin', 'Jl', 'Ju'):
             setattr(self, name, getattr(self.lat, name))
@@ -101,6 +118,8 @@ class tnac4o:
 
     def rotate_graph(self, rot=1):
         """quarter turns of the lattice, cumulative (tnac4o.py:290-340)"""
+        if self.mode == 'RMF':
+            return self._rotate_rmf(rot)
         for _ in range(rot):
             self.rotation += 1
             Nx, Ny, Nc = self.Nx, self.Ny, self.Nc
@@ -122,9 +141,40 @@ class tnac4o:
         self.rotation = np.mod(self.rotation, 4)
         self._divide_couplings()
 
+    def _rotate_rmf(self, rot):
+        """site (ny, nx) -> (Nx - 1 - nx, ny): factor keys, sizes and the cell order (tnac4o.py:315-336)"""
+        for _ in range(rot):      # (the reference does not advance `rotation` in this mode; kept: it only labels outputs)
+            Nx, Ny = self.Nx, self.Ny
+            turn = lambda ny, nx: (Nx - nx - 1, ny)
+            fac = {}
+            for key, val in self.J['fac'].items():
+                fac[turn(*key) if len(key) == 2 else turn(*key[:2]) + turn(*key[2:])] = val
+            sizes = np.zeros((Nx, Ny), dtype=int)
+            order_i = np.arange(Nx * Ny)
+            for nx in range(Nx):
+                for ny in range(Ny):
+                    sizes[Nx - nx - 1, ny] = self.Nrmf[ny, nx]
+                    order_i[ny * Nx + nx] = (Nx - nx - 1) * Ny + ny
+            self.Nx, self.Ny = Ny, Nx
+            self.order = order_i[self.order]
+            self.J['fac'] = fac
+            self.Nrmf = sizes
+        self.order_i[self.order] = np.arange(self.Nx * self.Ny)
+        self.rotation = np.mod(self.rotation, 4)
+        self._divide_couplings()
+
     def add_noise(self, amplitude=1e-7):
-        """tnac4o.py:917-933 (consumes the global numpy RNG like the reference)"""
+        """tnac4o.py:917-941 (consumes the global numpy RNG like the reference)"""
         self.logger.info('Adding noise to the coupling with ampliture %.2e', amplitude)
+        if self.mode == 'RMF':
+            fun = {}
+            for key, value in self.J['fun'].items():
+                fun[key] = np.array(value, dtype=float)
+                if fun[key].ndim == 1:
+                    fun[key] += ((np.random.rand(fun[key].shape[0]) * 2 - 1) * amplitude)
+            self.J['fun'] = fun
+            self._divide_couplings()
+            return
         nzr = self.J.nonzero()
         kk = ((np.random.rand(len(nzr[0])) * 2 - 1) * amplitude)
         self.J = scipy.sparse.lil_matrix(self.J)
@@ -675,8 +725,11 @@ class tnac4o:
         book = None
         if excitations_encoding > 1:
             from .droplets import AdjacencyDroplets
-            book = AdjacencyDroplets(excitations_encoding)
-            book.set_adjacency(self.J, [self.ind[ny][nx] for ny in range(self.Ny) for nx in range(self.Nx)])
+            book = AdjacencyDroplets(excitations_encoding, self.mode)
+            if self.mode == 'RMF':
+                book.set_grid(self.Nx, self.Ny)
+            else:
+                book.set_adjacency(self.J, [self.ind[ny][nx] for ny in range(self.Ny) for nx in range(self.Nx)])
         nsites = self.Nx * self.Ny
         self.logger.info('Searching ... ')
         for ny in range(self.Ny):
@@ -703,7 +756,10 @@ class tnac4o:
             book.finish(self.order_i, lim_hd)
             self.d, self.invd, self.el, self.free_d = book.d, book.invd, book.el, book.free_d
             # decoding works in the model's orientation (tnac4o.py:1131, 1356)
-            book.set_adjacency(self.J0, [self.ind0[ny][nx] for ny in range(self.Ny_model) for nx in range(self.Nx_model)])
+            if self.mode == 'RMF':
+                book.set_grid(self.Nx_model, self.Ny_model)
+            else:
+                book.set_adjacency(self.J0, [self.ind0[ny][nx] for ny in range(self.Ny_model) for nx in range(self.Nx_model)])
             self.adj = book.adj
             return self.energy
         self.el = self.el[0]
@@ -828,6 +884,9 @@ class tnac4o:
         return (exc[0], tuple(self._exc_cut_energy(se, maxdE - se[0][0]) for se in exc[1] if se[0][0] <= maxdE))
 
     def _exc_hd(self, dstate):
+        """tnac4o.py:2143-2150"""
+        if self.mode == 'RMF':
+            return sum(bin(int(st)).count('1') for st in dstate)
         return len(dstate)
 
     def _exc_get_unique_keys(self, excs):
@@ -849,8 +908,11 @@ class tnac4o:
     def _adjacency_book(self):
         """droplet structure of encodings 2 / 3 around the solver's (or a loaded file's) d / el / adj"""
         from .droplets import AdjacencyDroplets
-        book = AdjacencyDroplets(self.excitations_encoding)
-        book.set_adjacency(self.adj, [self.ind0[ny][nx] for ny in range(self.Ny_model) for nx in range(self.Nx_model)])
+        book = AdjacencyDroplets(self.excitations_encoding, self.mode)
+        if self.mode == 'RMF':
+            book.set_grid(self.Nx_model, self.Ny_model)
+        else:
+            book.set_adjacency(self.adj, [self.ind0[ny][nx] for ny in range(self.Ny_model) for nx in range(self.Nx_model)])
         book.d, book.invd, book.el, book.free_d = self.d, self.invd, self.el, self.free_d
         return book
 
@@ -964,6 +1026,8 @@ class tnac4o:
         """cell states -> spins: 1 up, 0 down, 2 inactive (tnac4o.py:261-286)"""
         ns = self.states.shape[0]
         ns = ns + number + 1 if number < 0 else min(number, ns)
+        if self.mode == 'RMF':
+            return self.states[:ns]
         out = np.zeros((ns, self.L), dtype=np.int8) + 2
         k = -1
         for ny in range(self.Ny_model):

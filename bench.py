@@ -119,41 +119,12 @@ def fp64_peak(torch, dev):
     return 2.0 * n ** 3 / best / 1e12
 
 
-def instrument_ops(ops, torch):
-    """wrap the primitive entry points with CUDA events on the launching stream (roofline pass only)"""
-    log = {'gemm': [], 'qr': [], 'svd': [], 'other': []}
-    raw = {}
-
-    def wrap(name, kind, flops=None):
-        fn = raw[name] = getattr(ops, name)
-
-        def timed(*a, **k):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            r = fn(*a, **k)
-            e1.record()
-            log[kind].append((flops(a, k) if flops else 0.0, e0, e1))
-            return r
-        setattr(ops, name, timed)
-
-    def gemm_flops(a, k):
-        A, B = a[0], a[1]
-        tA = k.get('transA', a[2] if len(a) > 2 else False)
-        tB = k.get('transB', a[3] if len(a) > 3 else False)
-        M = A.shape[1] if tA else A.shape[0]
-        K = A.shape[0] if tA else A.shape[1]
-        N = B.shape[0] if tB else B.shape[1]
-        return 2.0 * M * N * K
-    wrap('gemm', 'gemm', gemm_flops)
-    wrap('qr_pos', 'qr')
-    wrap('svd', 'svd')
-    for name in ('transpose', 'mpo_apply', 'pow2_scale_', 'truncation_rank', 'diff_norm'):
-        wrap(name, 'other')
-
-    def restore():
-        for name, fn in raw.items():
-            setattr(ops, name, fn)
-    return log, restore
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return {}
 
 
 def extra_configs(torch, dist, tnac4o_b200, parallel, dev, rank, world):
@@ -220,10 +191,14 @@ def run_gpu(args):
 
     from tnac4o_b200 import parallel
     B = args.batch
-    # one host thread per concurrent instance (it spins while it waits for its stream): never more threads than cores
+    # One host thread + one CUDA stream per concurrent instance.  Waiting threads sleep (cudaDeviceScheduleBlockingSync)
+    # instead of spinning, so the number of instances per GPU is not tied to the number of host cores: a thread needs
+    # ~0.3 s of CPU per instance for its ~10^5 launches.  Cap: 6 threads per core.
     cores = len(os.sched_getaffinity(0))
-    if world * (B + 1) > cores:
-        B = max(2, cores // world - 1)
+    from tnac4o_b200._native import lib as _lib, check as _check
+    _check(_lib.tn_set_blocking_sync(1))
+    if world * B > 6 * cores:
+        B = max(2, 6 * cores // world)
     J = instance_couplings(rank * B)
     t_prep = time.time()
     inss = [tnac4o_b200.tnac4o(mode='Ising', Nx=CFG['Nx'], Ny=CFG['Ny'], Nc=CFG['Nc'], J=instance_couplings(rank * B + i),
@@ -302,33 +277,46 @@ def run_gpu(args):
     lat_stats = lat_runs[-1][2]
 
     def roofline_pass():
-        """one extra, instrumented single-instance step (not part of the timed region): CUDA events around every primitive"""
+        """one extra single-instance step on the NATIVE path (the path the timed region runs) with the library's own
+        per-primitive timers on: CUDA events on the launching stream around every primitive call of csrc/mps_native.cu
+        and csrc/search_native.cu, each tagged with its algorithmic flops / bytes"""
+        from tnac4o_b200._native import Context
         peak = fp64_peak(torch, dev)
-        log, restore = instrument_ops(ops, torch)
-        ins.native_rows = False        # same kernel sequence as the native row driver, but every primitive call is visible
+        hbm_peak = measured_peaks().get('hbm_gbs', 6533.2)
+        ctx = Context.get(dev)
+        ctx.profile(True)
         t_pass = step(False, [ins])[0]
-        torch.cuda.synchronize(dev)
-        restore()
-        ins.native_rows = True
-        secs = {k: sum(a.elapsed_time(b) for _, a, b in v) * 1e-3 for k, v in log.items()}
-        flops = sum(f for f, _, _ in log['gemm'])
-        big = [(f, a.elapsed_time(b) * 1e-3) for f, a, b in log['gemm'] if f >= 1e9]
-        gsec = secs['gemm']
-        roofline = {'bound': 'tensor', 'kernel': 'gemm_kernel (DMMA m8n8k4 f64), the contraction kernel',
-                    'achieved': flops / gsec / 1e12 if gsec else None,
-                    'peak': peak, 'unit': 'TFLOP/s', 'frac': (flops / gsec / 1e12 / peak) if gsec else None,
-                    'traffic': NCU_TRAFFIC_LARGE_GEMM['bytes'], 'traffic_note': NCU_TRAFFIC_LARGE_GEMM['note'],
-                    'launches': len(log['gemm']), 'gemm_seconds_per_instance': gsec,
-                    'achieved_large_gemms': (sum(f for f, _ in big) / sum(t for _, t in big) / 1e12) if big else None,
-                    'frac_large_gemms': (sum(f for f, _ in big) / sum(t for _, t in big) / 1e12 / peak) if big else None,
-                    'device_seconds_by_primitive_single_instance': {k: round(v, 4) for k, v in secs.items()},
-                    'instrumented_instance_seconds': t_pass,
-                    'note': 'by device time the step is dominated by the latency-bound factorisations (cluster Householder panels, '
-                            'cluster Jacobi rounds), which are neither HBM- nor tensor-bound; the GEMM is the contraction kernel the '
-                            'roofline applies to',
-                    'peak_source': 'measured here: torch.matmul f64 8192^3 (cuBLAS DGEMM), best of 5 -- MEASURED_PEAKS.json has no FP64 entry',
-                    'measured_in': 'one extra instrumented single-instance step after the timed region (CUDA events around every primitive call)'}
-        return roofline
+        prof = ctx.profile_read()
+        ctx.profile(False)
+        per = {}
+        for name, r in prof.items():
+            sec = r['seconds']
+            per[name] = {'seconds': round(sec, 5), 'calls': int(r['calls']), 'gflop': round(r['flops'] / 1e9, 3),
+                         'tflops': (r['flops'] / sec / 1e12) if sec > 0 and r['flops'] else None,
+                         'frac_fp64_tensor_peak': (r['flops'] / sec / 1e12 / peak) if sec > 0 and r['flops'] else None,
+                         'gbytes': round(r['bytes'] / 1e9, 3),
+                         'frac_hbm_peak': (r['bytes'] / sec / 1e9 / hbm_peak) if sec > 0 and r['bytes'] else None}
+        contraction = ('gemm', 'qr', 'svd', 'right_env')
+        flops = sum(prof[k]['flops'] for k in contraction)
+        secs = sum(prof[k]['seconds'] for k in contraction)
+        allsec = sum(r['seconds'] for r in prof.values())
+        dominant = max(prof, key=lambda k: prof[k]['seconds'])
+        return {'bound': 'tensor', 'kernel': 'boundary-MPS contraction kernels of one instance on the native path: DMMA GEMM (gemm_kernel), '
+                                             'cluster Householder QR (qr_panel_reg_kernel + DMMA updates), cluster Jacobi SVD, right environments',
+                'achieved': flops / secs / 1e12 if secs else None, 'peak': peak, 'unit': 'TFLOP/s',
+                'frac': (flops / secs / 1e12 / peak) if secs else None,
+                'traffic': NCU_TRAFFIC_LARGE_GEMM['bytes'], 'traffic_note': NCU_TRAFFIC_LARGE_GEMM['note'],
+                'algorithmic_gflop_per_instance': round(flops / 1e9, 2), 'device_seconds_contraction': secs,
+                'device_seconds_all_primitives': allsec, 'dominant_primitive_by_device_time': dominant,
+                'per_primitive': per, 'instrumented_instance_seconds': t_pass,
+                'hbm_peak_gbs': hbm_peak,
+                'note': 'achieved = algorithmic flops of the reference schedule that were executed (QR 4mn^2 - 4n^3/3 incl. forming Q, SVD 22k^3 '
+                        'with vectors / 8k^3/3 without, GEMM 2MNK, right environments) / device time of those primitives, single instance, '
+                        'one stream; QR panels and Jacobi rounds run on the non-tensor FP64 pipe (measured ~15 FMA/clk/SM, '
+                        'profiles/r2a_qr_panel_phase_cycles_and_svd_timings.txt) and are latency-bound, the GEMMs run on DMMA',
+                'peak_source': 'measured here: torch.matmul f64 8192^3 (cuBLAS DGEMM), best of 5 -- MEASURED_PEAKS.json has no FP64 entry',
+                'measured_in': 'one extra single-instance step on the native path right after the timed region, library timers on '
+                               '(tn_profile: CUDA events on the launching stream around every primitive call)'}
 
     roofline = roofline_pass() if rank == 0 else None      # before the one-off heavy runs below: same thermal state as the timed region
     # ---- BASELINE configs 4 and 5 as quoted (outside the timed region): ONE search at M = 2^12 with its branch batch
@@ -359,6 +347,16 @@ def run_gpu(args):
     from conftest import droplet_golden
     e_file, _ = droplet_golden(CFG['L'], 1)
     parity_ok = bool(abs(ins.energy[0] - e_file) < 1e-5)
+    # ... and on every synthetic instance of the batch: the search's own energy against the independent CSR energy kernel
+    # on the returned configuration (auxx.energy_Jij), i.e. energy bookkeeping and state decoding agree on all of them
+    synth_ok = True
+    for i, x in enumerate(inss):
+        Ji = instance_couplings(rank * B + i)
+        synth_ok = synth_ok and bool(abs(tnac4o_b200.energy_Jij(Ji, x.binary_states()[:1])[0] - x.energy[0]) < 1e-6)
+    if roofline is not None and roofline.get('algorithmic_gflop_per_instance'):
+        whole = roofline['algorithmic_gflop_per_instance'] * 1e9 * instances / total / 1e12
+        roofline['whole_step_tflops'] = whole
+        roofline['whole_step_frac_fp64_tensor_peak'] = whole / (roofline['peak'] * world)
 
     # ---- CPU baseline: the numpy port of the reference on a bounded sample
     cpu = cpu_sample(J)
@@ -367,8 +365,9 @@ def run_gpu(args):
            'dtype': 'f64', 'data': 'droplet instance 001 (rank 0) + synthetic couplings on the same chimera pattern (other ranks)',
            'config': {'workload': 'e01 ground-state search L=2048 (16x16x8 chimera), M=2^10, Dmax=32, beta=3, P_cutoff=1e-8, no preconditioning',
                       'batch_per_gpu': B, 'batch_requested': args.batch, 'host_cores': cores,
-                      'concurrency': 'one host thread + one CUDA stream per instance',
-                      'l2': 'flushed between steps (256 MiB write)', 'parity_energy_matches_golden': parity_ok},
+                      'concurrency': 'one host thread + one CUDA stream per instance, blocking host waits',
+                      'l2': 'flushed between steps (256 MiB write)', 'parity_energy_matches_golden': parity_ok,
+                      'parity_synthetic_instances_self_consistent': synth_ok},
            'latency_seconds_single_instance': lat,
            'seconds_rhoT_per_instance_under_concurrency': float(np.mean([s['seconds_rhoT'] for s in stats])) / B,
            'seconds_search_per_instance_under_concurrency': float(np.mean([s['seconds_search'] for s in stats])) / B,

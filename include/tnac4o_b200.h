@@ -43,6 +43,16 @@ int tn_create(int device, tn_ctx** out);
 int tn_destroy(tn_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t tn_launch_count(const tn_ctx* ctx);
+/* Per-primitive timing of the native drivers (tn_row_compress, tn_search_ground_state): while enabled, every primitive
+ * call is bracketed by CUDA events on the launching stream and tagged with its algorithmic flops / bytes.
+ * tn_profile_read synchronises and returns, per category c < ncat (0 gemm, 1 qr, 2 svd, 3 other boundary-MPS kernels,
+ * 4 right environments, 5 marginals, 6 select/merge/top-M), h_out[4c..4c+3] = seconds, flops, bytes, calls.  The
+ * reference's counterpart is the time.time() deltas it logs per phase (tnac4o.py:407-415, 430-431). */
+int tn_profile(tn_ctx* ctx, int on);
+int tn_profile_read(tn_ctx* ctx, double* h_out, int ncat);
+/* cudaDeviceScheduleBlockingSync for the current device: waiting host threads sleep instead of spinning (the reference is
+ * single-threaded; this is for running many solver instances per GPU from fewer host cores) */
+int tn_set_blocking_sync(int on);
 
 /* ---------------------------------------------------------------- boundary-MPS primitives (tnac4o/mps.py) */
 
@@ -225,6 +235,26 @@ int tn_xor_diff(tn_ctx* ctx, void* stream, int npairs, int nsites, int pos, cons
 int tn_apply_droplets(tn_ctx* ctx, void* stream, int nstates, int nsites, const uint8_t* ground, const int32_t* flip_ptr,
                       const int32_t* flip_key, const int32_t* drop_ptr, const int16_t* drop_pos, const uint8_t* drop_xor,
                       uint8_t* out);
+
+/* Droplet bookkeeping of the spectrum search with excitations_encoding = 1 on the device -- replaces the per-site host
+ * loops of _search_low_energy_spectrum_v1 (tnac4o.py:844-893): dictionary of droplet shapes (_exc_add_to_d, 2051-2069) as
+ * a hash table + CSR pool, excitation lists `el` as node / children / list pools, energy pruning (_exc_cut_energy,
+ * 2071-2079) as lazily composed budgets.  tn_book_site is called once per lattice site after tn_merge / tn_topm /
+ * tn_materialise with the arrays those calls produced (device pointers; `order` = low words of the sorted merge keys,
+ * copied before tn_topm; old_states = state rows of the branches BEFORE the site; lim_hd > 1 drops droplets touching
+ * fewer cells, lim_hd < -1 droplets with fewer than -lim_hd set pattern bits -- the RMF rule of _exc_hd, 2143-2150); it
+ * synchronises twice (pair count, pool growth).  tn_book_sizes / tn_book_export hand the pools to the host once, after the last site. */
+typedef struct tn_book tn_book;
+int tn_book_create(tn_ctx* ctx, void* stream, int nsites, int M, tn_book** out);
+int tn_book_site(tn_ctx* ctx, tn_book* book, int site, int K, int Bn, const int32_t* order, const int32_t* g_rep,
+                 const int32_t* g_start, const int32_t* g_size, const double* g_E, const double* g_prob, const int32_t* sel,
+                 const double* Enew, const double* Pnew, const int32_t* parent, const int32_t* cell, const uint8_t* old_states,
+                 double max_dEng, int lim_hd);
+int tn_book_sizes(tn_ctx* ctx, tn_book* book, int64_t* h_sizes);
+int tn_book_export(tn_ctx* ctx, tn_book* book, double* h_dE, double* h_dP, int32_t* h_key, int32_t* h_first, int32_t* h_last,
+                   int32_t* h_cptr, int32_t* h_ccnt, int32_t* h_cnode, double* h_cbud, int32_t* h_sptr, int16_t* h_spos,
+                   uint8_t* h_sxor, int32_t* h_list0);
+int tn_book_free(tn_book* book);
 
 /* Enumeration of all droplet combinations of an excitation tree (excitations_encoding = 1) with excitation energy
  * <= max_dEng, at most max_states (the lowest), sorted by energy -- replaces the Python loop _exc_unpack_v1

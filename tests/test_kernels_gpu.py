@@ -15,7 +15,10 @@ def up(a, dtype=None):
 
 
 @pytest.mark.parametrize('M,N,K', [(1, 1, 1), (7, 5, 3), (64, 64, 16), (130, 70, 33), (512, 512, 512), (1024, 257, 96),
-                                   (32, 480, 8192), (16, 16, 4096), (2048, 128, 512), (57, 59, 39)])
+                                   (32, 480, 8192), (16, 16, 4096), (2048, 128, 512), (57, 59, 39),
+                                   # >= 148 tiles of 128 x 128: the TMA-staged kernel (gemm_tma.cu) for the untransposed case,
+                                   # with ragged M / N / K edges that the hardware zero-fills
+                                   (8192, 512, 512), (4000, 650, 100), (2500, 1300, 78)])
 @pytest.mark.parametrize('tA,tB', [(False, False), (True, False), (False, True), (True, True)])
 def test_gemm(M, N, K, tA, tB):
     from tnac4o_b200 import ops

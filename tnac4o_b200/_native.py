@@ -34,6 +34,9 @@ _SIGS = {
     'tn_create': (c_int, [c_int, POINTER(c_void_p)]),
     'tn_destroy': (c_int, [P]),
     'tn_launch_count': (c_int64, [P]),
+    'tn_profile': (c_int, [P, c_int]),
+    'tn_profile_read': (c_int, [P, P, c_int]),
+    'tn_set_blocking_sync': (c_int, [c_int]),
     'tn_gemm': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_double, P, c_int, c_int64, P, c_int, c_int64,
                         c_double, P, c_int, c_int64, c_int]),
     'tn_transpose': (c_int, [P, P, c_int, c_int, P, c_int, P, c_int]),
@@ -68,6 +71,11 @@ _SIGS = {
     'tn_xor_diff': (c_int, [P, P, c_int, c_int, c_int, P, P, P, P, P, P, P, P]),
     'tn_apply_droplets': (c_int, [P, P, c_int, c_int, P, P, P, P, P, P, P]),
     'tn_energy_ising': (c_int, [P, P, c_int, c_int, P, c_int64, P, P, P, P]),
+    'tn_book_create': (c_int, [P, P, c_int, c_int, POINTER(c_void_p)]),
+    'tn_book_site': (c_int, [P, P, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P, P, c_double, c_int]),
+    'tn_book_sizes': (c_int, [P, P, P]),
+    'tn_book_export': (c_int, [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P]),
+    'tn_book_free': (c_int, [P]),
     'tn_decode_enumerate': (c_int, [P, P, c_int, c_int, P, P, P, P, P, P, c_double, c_int64, POINTER(c_void_p),
                                     POINTER(c_int64)]),
     'tn_decode_fetch': (c_int, [P, P, c_int64, P, P, P, P, P, P]),
@@ -94,6 +102,7 @@ class Context:
     memory, so concurrent solver instances -- one host thread and one CUDA stream each -- never share one."""
 
     _by_key = {}
+    _retired = {}
     _lock = threading.Lock()
 
     def __init__(self, device_index):
@@ -108,10 +117,11 @@ class Context:
 
     @classmethod
     def get(cls, device=None):
-        if device is None:
+        if device is None or torch.device(device).index is None:
+            # torch.device('cuda') has no index: it means the CURRENT device, not device 0
             index = torch.cuda.current_device() if torch.cuda.is_available() else 0
         else:
-            index = torch.device(device).index or 0
+            index = torch.device(device).index
         key = (index, threading.get_ident())
         ctx = cls._by_key.get(key)
         if ctx is None:
@@ -123,9 +133,23 @@ class Context:
 
     @classmethod
     def total_launches(cls, device=None):
-        index = torch.cuda.current_device() if device is None else (torch.device(device).index or 0)
+        index = torch.device(device).index if device is not None else None
+        if index is None:
+            index = torch.cuda.current_device()
         with cls._lock:
-            return sum(c.launch_count() for (i, _), c in cls._by_key.items() if i == index)
+            return sum(c.launch_count() for (i, _), c in cls._by_key.items() if i == index) + cls._retired.get(index, 0)
+
+    @classmethod
+    def release_thread(cls):
+        """destroy the contexts of the calling host thread (scratch, pinned buffer, memory pool); their launch counts stay
+        in the per-device total.  Called by worker threads of parallel.StreamPool before they exit."""
+        me = threading.get_ident()
+        with cls._lock:
+            mine = [k for k in cls._by_key if k[1] == me]
+            for k in mine:
+                c = cls._by_key.pop(k)
+                cls._retired[k[0]] = cls._retired.get(k[0], 0) + c.launch_count()
+                lib.tn_destroy(c.handle)
 
     @property
     def stream(self):
@@ -133,6 +157,20 @@ class Context:
 
     def launch_count(self):
         return int(lib.tn_launch_count(self.handle))
+
+    PROFILE_CATEGORIES = ('gemm', 'qr', 'svd', 'mps_other', 'right_env', 'marginals', 'select_merge')
+
+    def profile(self, on=True):
+        """start (and reset) / stop the per-primitive timing of the native drivers on this context"""
+        check(lib.tn_profile(self.handle, int(bool(on))))
+
+    def profile_read(self):
+        """{category: {'seconds', 'flops', 'bytes', 'calls'}} accumulated since profile(True); synchronises"""
+        n = len(self.PROFILE_CATEGORIES)
+        buf = (c_double * (4 * n))()
+        check(lib.tn_profile_read(self.handle, buf, n))
+        return {name: dict(zip(('seconds', 'flops', 'bytes', 'calls'), buf[4 * i:4 * i + 4]))
+                for i, name in enumerate(self.PROFILE_CATEGORIES)}
 
 
 def ptr(t):

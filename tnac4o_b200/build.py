@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'lib')
 LIB = os.path.join(OUT, 'libtnac4o_b200.so')
-SOURCES = ['api.cu', 'gemm.cu', 'qr.cu', 'svd.cu', 'mps_ops.cu', 'mps_native.cu', 'sort.cu', 'search.cu', 'search_native.cu', 'droplet.cu', 'decode.cu']
+SOURCES = ['api.cu', 'gemm.cu', 'gemm_tma.cu', 'qr.cu', 'svd.cu', 'mps_ops.cu', 'mps_native.cu', 'sort.cu', 'search.cu', 'search_native.cu', 'droplet.cu', 'droplet_book.cu', 'decode.cu']
 HEADERS = [os.path.join(CSRC, 'common.cuh'), os.path.join(HERE, '..', 'include', 'tnac4o_b200.h')]
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC']

@@ -98,6 +98,13 @@ int tn_create(int device, tn_ctx** out) {
         delete ctx;
         return TN_ERR_NOMEM;
     }
+    e = cudaMalloc(&ctx->counters, 4096);
+    if (e == cudaSuccess) e = cudaMemset(ctx->counters, 0, 4096);
+    if (e != cudaSuccess) {
+        cudaFreeHost(ctx->pinned);
+        delete ctx;
+        return tn_cuda_fail(e, "cudaMalloc(counters)", __FILE__, __LINE__);
+    }
     *out = ctx;
     return TN_OK;
 }
@@ -108,11 +115,47 @@ int tn_destroy(tn_ctx* ctx) {
     for (int i = 0; i < tn_ctx::SLOTS; ++i)
         if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->pool) { cudaDeviceSynchronize(); cudaMemPoolDestroy(ctx->pool); }
     delete ctx;
     return TN_OK;
 }
 
 int64_t tn_launch_count(const tn_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int tn_profile(tn_ctx* ctx, int on) {
+    TN_REQUIRE(ctx != nullptr, "null context");
+    for (auto& r : ctx->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    ctx->prof_recs.clear();
+    for (int c = 0; c < TN_P_COUNT; ++c)
+        for (int k = 0; k < 4; ++k) ctx->prof_acc[c][k] = 0.0;
+    ctx->prof_on = on != 0;
+    return TN_OK;
+}
+
+int tn_profile_read(tn_ctx* ctx, double* h_out, int ncat) {
+    TN_REQUIRE(ctx != nullptr && h_out != nullptr && ncat >= 1, "bad arguments");
+    for (auto& r : ctx->prof_recs) {
+        TN_CUDA(cudaEventSynchronize(r.e1));
+        float ms = 0.f;
+        TN_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+        ctx->prof_acc[r.cat][0] += 1e-3 * ms;
+        ctx->prof_acc[r.cat][1] += r.flops;
+        ctx->prof_acc[r.cat][2] += r.bytes;
+        ctx->prof_acc[r.cat][3] += 1.0;
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    ctx->prof_recs.clear();
+    for (int c = 0; c < ncat && c < TN_P_COUNT; ++c)
+        for (int k = 0; k < 4; ++k) h_out[c * 4 + k] = ctx->prof_acc[c][k];
+    return TN_OK;
+}
+
+int tn_set_blocking_sync(int on) {
+    // host threads waiting in a synchronising call sleep instead of spinning: many solver threads can share few cores
+    TN_CUDA(cudaSetDeviceFlags(on ? cudaDeviceScheduleBlockingSync : cudaDeviceScheduleAuto));
+    return TN_OK;
+}
 
 }  // extern "C"

@@ -4,10 +4,24 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 
 #include "../../include/tnac4o_b200.h"
 
+// ---- optional per-primitive timing of the native drivers (tn_profile / tn_profile_read): CUDA events on the launching
+// stream around every primitive call of csrc/mps_native.cu and csrc/search_native.cu, with the algorithmic flops and
+// bytes of the call -- the numbers bench.py's roofline is computed from
+enum { TN_P_GEMM = 0, TN_P_QR, TN_P_SVD, TN_P_MPS_OTHER, TN_P_RR, TN_P_MARGINALS, TN_P_SELECT_MERGE, TN_P_COUNT };
+struct tn_prof_rec {
+    int cat;
+    double flops, bytes;
+    cudaEvent_t e0, e1;
+};
+
 struct tn_ctx {
+    bool prof_on = false;
+    std::vector<tn_prof_rec> prof_recs;
+    double prof_acc[TN_P_COUNT][4] = {};      // seconds, flops, bytes, calls
     int device = 0;
     int sm_count = 148;
     static constexpr int SLOTS = 7;   // independent grow-only device scratch areas
@@ -16,6 +30,7 @@ struct tn_ctx {
     uint64_t scratch_gen = 0;         // bumped whenever a slot is reallocated (captured graphs hold slot pointers)
     bool capturing = false;           // a stream capture is in progress: slots must not be reallocated
     void* pinned = nullptr;           // small pinned host buffer for scalar read-backs
+    void* counters = nullptr;         // 1024 zero-initialised device words: "last CTA reduces" tickets (reset by their user)
     cudaMemPool_t pool = nullptr;     // private stream-ordered pool: no cross-stream reuse, hence no hidden dependencies
                                       // between the streams of concurrent solver instances
     int64_t launches = 0;
@@ -54,6 +69,25 @@ void tn_capture_unlock();
     } while (0)
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+struct tn_prof_scope {
+    tn_ctx* ctx;
+    cudaStream_t st;
+    size_t idx = 0;
+    bool on;
+    tn_prof_scope(tn_ctx* c, cudaStream_t s, int cat, double flops, double bytes) : ctx(c), st(s), on(c && c->prof_on) {
+        if (!on) return;
+        tn_prof_rec r{cat, flops, bytes, nullptr, nullptr};
+        cudaEventCreate(&r.e0);
+        cudaEventCreate(&r.e1);
+        cudaEventRecord(r.e0, st);
+        idx = ctx->prof_recs.size();
+        ctx->prof_recs.push_back(r);
+    }
+    ~tn_prof_scope() {
+        if (on) cudaEventRecord(ctx->prof_recs[idx].e1, st);
+    }
+};
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // ---- device helpers ---------------------------------------------------------------------------

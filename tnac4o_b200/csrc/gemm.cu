@@ -216,6 +216,9 @@ int launch_cfg(tn_ctx* ctx, cudaStream_t st, int tA, int tB, int M, int N, int K
 
 }  // namespace
 
+int tn_gemm_tma_try(tn_ctx* ctx, cudaStream_t st, int M, int N, int K, double alpha, const double* A, int lda, const double* B,
+                    int ldb, double beta, double* C, int ldc);
+
 // internal entry used by the other translation units (qr.cu)
 int tn_gemm_impl(tn_ctx* ctx, cudaStream_t st, int tA, int tB, int M, int N, int K, double alpha, const double* A,
                  int lda, int64_t sA, const double* B, int ldb, int64_t sB, double beta, double* C, int ldc, int64_t sC,
@@ -223,8 +226,14 @@ int tn_gemm_impl(tn_ctx* ctx, cudaStream_t st, int tA, int tB, int M, int N, int
     if (M <= 0 || N <= 0 || batch <= 0) return TN_OK;
     // big tile when it still fills the machine, small tile otherwise
     int big_tiles = ceil_div(M, 128) * ceil_div(N, 128) * batch;
-    if (big_tiles >= ctx->sm_count && M >= 128 && N >= 128)
+    if (big_tiles >= ctx->sm_count && M >= 128 && N >= 128) {
+        if (!tA && !tB && batch == 1) {
+            // TMA-staged operands (gemm_tma.cu) when the operands are 16-byte aligned; 1 = launched, 0 = not eligible
+            const int rc = tn_gemm_tma_try(ctx, st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+            if (rc != 0) return rc < 0 ? rc : TN_OK;
+        }
         return launch_cfg<128, 128, 32, 64>(ctx, st, tA, tB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
+    }
     return launch_cfg<64, 64, 32, 32>(ctx, st, tA, tB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
 }
 

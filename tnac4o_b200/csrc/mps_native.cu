@@ -101,7 +101,17 @@ struct Mps {
         return TN_OK;
     }
     int gemm(int tA, int tB, int M, int N, int K, const double* a, int lda, const double* b, int ldb, double* c, int ldc) {
+        tn_prof_scope prof(ctx, st, TN_P_GEMM, 2.0 * M * N * K, 8.0 * ((double)M * K + (double)K * N + (double)M * N));
         return tn_gemm_impl(ctx, st, tA, tB, M, N, K, 1.0, a, lda, 0, b, ldb, 0, 0.0, c, ldc, 0, 1);
+    }
+    // algorithmic flops of an economic QR with explicit Q (dgeqrf + dorgqr) and of an SVD
+    static double qr_flops(double m, double n) {
+        const double k = m < n ? m : n;
+        return 4.0 * m * n * k - 2.0 * (m + n) * k * k + 4.0 / 3.0 * k * k * k;
+    }
+    static double svd_flops(double m, double n, bool vectors) {
+        const double k = m < n ? m : n;
+        return vectors ? 22.0 * k * k * k : 8.0 / 3.0 * k * k * k;
     }
 
     // ---- moving the centre (mps.py:368-380, 532-548, 772-800)
@@ -126,7 +136,11 @@ struct Mps {
         const int m = a.Dl * a.d, nn = a.Dr, k = m < nn ? m : nn;
         Buf Q, Rm, bits;
         TRY(Q.alloc((int64_t)m * k, st)); TRY(Rm.alloc((int64_t)k * nn, st)); TRY(bits.alloc(1, st));
-        TRY(tn_qr_pos(ctx, st, m, nn, a.b.p, nn, Q.p, k, Rm.p, nn, (unsigned long long*)bits.p));
+        {
+            tn_prof_scope prof(ctx, st, TN_P_QR, qr_flops(m, nn), 8.0 * (2.0 * m * nn + (double)k * nn));
+            TRY(tn_qr_pos(ctx, st, m, nn, a.b.p, nn, Q.p, k, Rm.p, nn, (unsigned long long*)bits.p));
+        }
+        tn_prof_scope prof(ctx, st, TN_P_MPS_OTHER, 0.0, 16.0 * k * nn);
         TRY(tn_pow2_scale(ctx, st, Rm.p, (int64_t)k * nn, (const unsigned long long*)bits.p, log2norm.p));
         a.b = std::move(Q); a.Dr = k;
         C.b = std::move(Rm); C.r = k; C.c = nn;
@@ -138,9 +152,16 @@ struct Mps {
         const int rows = a.d * a.Dr, cols = a.Dl, k = rows < cols ? rows : cols;      // QR of the (d Dr) x Dl transpose
         Buf At, Q, Rm, bits, Qt, Ct;
         TRY(At.alloc((int64_t)rows * cols, st));
-        TRY(tn_transpose(ctx, st, cols, rows, a.b.p, rows, At.p, cols));
+        {
+            tn_prof_scope prof(ctx, st, TN_P_MPS_OTHER, 0.0, 16.0 * rows * cols);
+            TRY(tn_transpose(ctx, st, cols, rows, a.b.p, rows, At.p, cols));
+        }
         TRY(Q.alloc((int64_t)rows * k, st)); TRY(Rm.alloc((int64_t)k * cols, st)); TRY(bits.alloc(1, st));
-        TRY(tn_qr_pos(ctx, st, rows, cols, At.p, cols, Q.p, k, Rm.p, cols, (unsigned long long*)bits.p));
+        {
+            tn_prof_scope prof(ctx, st, TN_P_QR, qr_flops(rows, cols), 8.0 * (2.0 * rows * cols + (double)k * cols));
+            TRY(tn_qr_pos(ctx, st, rows, cols, At.p, cols, Q.p, k, Rm.p, cols, (unsigned long long*)bits.p));
+        }
+        tn_prof_scope prof(ctx, st, TN_P_MPS_OTHER, 0.0, 16.0 * ((double)k * cols * 2 + (double)rows * k));
         TRY(tn_pow2_scale(ctx, st, Rm.p, (int64_t)k * cols, (const unsigned long long*)bits.p, log2norm.p));
         TRY(Qt.alloc((int64_t)k * rows, st));
         TRY(tn_transpose(ctx, st, rows, k, Q.p, k, Qt.p, rows));
@@ -158,7 +179,10 @@ struct Mps {
         Buf U, Sv, Vt;
         TRY(U.alloc((int64_t)m * k, st)); TRY(Sv.alloc(k, st)); TRY(Vt.alloc((int64_t)k * n, st));
         int sweeps = 0;
-        TRY(tn_svd(ctx, st, m, n, C.b.p, n, U.p, k, Sv.p, Vt.p, n, 1, &sweeps));
+        {
+            tn_prof_scope prof(ctx, st, TN_P_SVD, svd_flops(m, n, true), 8.0 * (3.0 * m * n));
+            TRY(tn_svd(ctx, st, m, n, C.b.p, n, U.p, k, Sv.p, Vt.p, n, 1, &sweeps));
+        }
         const double eps = 2.220446049250313e-16;
         int keep = 0;
         double lost = 0.0;
@@ -252,7 +276,10 @@ struct Mps {
         TRY(Sn.b.alloc(k, st));
         Sn.r = 1; Sn.c = k;
         int sweeps = 0;
-        TRY(tn_svd(ctx, st, C.r, C.c, C.b.p, C.c, nullptr, 1, Sn.b.p, nullptr, 1, 0, &sweeps));
+        {
+            tn_prof_scope prof(ctx, st, TN_P_SVD, svd_flops(C.r, C.c, false), 8.0 * C.r * C.c);
+            TRY(tn_svd(ctx, st, C.r, C.c, C.b.p, C.c, nullptr, 1, Sn.b.p, nullptr, 1, 0, &sweeps));
+        }
         if (S[pC].c != k) TRY(unit_S(S[pC], k));
         TRY(tn_diff_norm(ctx, st, S[pC].b.p, Sn.b.p, k, dS));
         S[pC] = std::move(Sn);
@@ -347,7 +374,10 @@ int tn_row_compress(tn_ctx* ctx, void* stream, int L, const double* const* A_in,
         Ten& a = row->psi.A[n];
         a.Dl = Dl[n] * wl[n]; a.d = du[n]; a.Dr = Dr[n] * wr[n];
         rc = a.b.alloc((int64_t)a.Dl * a.d * a.Dr, st);
-        if (!rc) rc = tn_mpo_apply(ctx, st, conj, Dl[n], dphys[n], Dr[n], wl[n], wr[n], du[n], A_in[n], W[n], a.b.p);
+        if (!rc) {
+            tn_prof_scope prof(ctx, st, TN_P_MPS_OTHER, 2.0 * a.Dl * a.d * a.Dr * dphys[n], 8.0 * a.Dl * a.d * a.Dr);
+            rc = tn_mpo_apply(ctx, st, conj, Dl[n], dphys[n], Dr[n], wl[n], wr[n], du[n], A_in[n], W[n], a.b.p);
+        }
     }
     if (!rc) rc = row->psi.compress(Dmax, tolS, tolV, max_sweeps, graduate, &row->overlap);
     if (rc) { cudaStreamSynchronize(st); delete row; return rc; }

@@ -47,11 +47,14 @@ __device__ long long g_phase[16];
 #define PH(k) do { } while (0)
 #endif
 
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(RT, 1)
+// The cluster size is a launch attribute: 1, 2, 4 or 8 CTAs, the smallest that gives every row a register slot
+// (RT * RPT rows per CTA).  A single CTA needs no cluster traffic at all.
+__global__ void __launch_bounds__(RT, 1)
 qr_panel_reg_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, double* __restrict__ Vall, int ldv,
                     double* __restrict__ Tout) {
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
+    const int ncl = (int)cluster.num_blocks();
     __shared__ double red[RT / 32][JB];
     __shared__ double cw[2][CL][JB];          // per-CTA partial dots, double-buffered by column parity
     __shared__ double prow[2][JB];            // pivot row broadcast
@@ -62,7 +65,7 @@ qr_panel_reg_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, doub
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m_rem = m - j0;
-    const int rows_per = (m_rem + CL - 1) / CL;
+    const int rows_per = (m_rem + ncl - 1) / ncl;
     int rel[RPT];
     bool have[RPT];
     double row[RPT][JB];
@@ -76,7 +79,7 @@ qr_panel_reg_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, doub
     }
     if (tid < JB * JB) Ts[tid] = 0.0;
     // every CTA of the cluster must have started before anyone writes into its shared memory
-    cluster.sync();
+    if (ncl > 1) cluster.sync(); else __syncthreads();
 
     // The register file of every thread is ROTATED by one column per step, so the current column is always slot 0,
     // the columns still to be updated are slots 1 .. 15-j and the finished reflectors are slots 16-j .. 15.  The loop
@@ -138,26 +141,25 @@ qr_panel_reg_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, doub
         PH(2);
         __syncthreads();
         PH(3);
-        if (tid < JB) {
+        if (tid < 32) {
+            // lanes 0-15 and 16-31 hold the same column sums; the two half-warps share the remote stores
+            const int c = tid & 15;
             double s = 0.0;
 #pragma unroll
-            for (int w = 0; w < RT / 32; ++w) s += red[w][tid];
-#pragma unroll
-            for (int r = 0; r < CL; ++r) *cluster.map_shared_rank(&cw[buf][rank][tid], r) = s;
+            for (int w = 0; w < RT / 32; ++w) s += red[w][c];
+            for (int r = (tid >> 4); r < ncl; r += 2) *cluster.map_shared_rank(&cw[buf][rank][c], r) = s;
             if (rank == owner) {
-                const double pv = stage[tid];
-#pragma unroll
-                for (int r = 0; r < CL; ++r) *cluster.map_shared_rank(&prow[buf][tid], r) = pv;
+                const double pv = stage[c];
+                for (int r = (tid >> 4); r < ncl; r += 2) *cluster.map_shared_rank(&prow[buf][c], r) = pv;
             }
         }
         PH(4);
-        cluster.sync();
+        if (ncl > 1) cluster.sync(); else __syncthreads();
         PH(5);
         // ---- reflector parameters, tau * v^T a_slot and column j of T: 16 lanes, redundant scalar work
         if (tid < JB) {
             double wc = 0.0, w0 = 0.0;
-#pragma unroll
-            for (int r = 0; r < CL; ++r) { wc += cw[buf][r][tid]; w0 += cw[buf][r][0]; }
+            for (int r = 0; r < ncl; ++r) { wc += cw[buf][r][tid]; w0 += cw[buf][r][0]; }
             const double alpha = prow[buf][0];
             double beta, tau, scale;
             if (w0 == 0.0) { beta = alpha; tau = 0.0; scale = 0.0; }
@@ -429,10 +431,26 @@ __global__ void qr_finish_kernel(const double* __restrict__ A, int lda, int m, i
 }
 
 int launch_panel(tn_ctx* ctx, cudaStream_t st, double* A, int lda, int m, int j0, int jb, double* Vall, int ldv, double* T) {
-    const int rows_per = ceil_div(m - j0, CL);
-    if (rows_per <= RT * RPT) {
-        qr_panel_reg_kernel<<<CL, RT, 0, st>>>(A, lda, m, j0, jb, Vall, ldv, T);
+    const int m_rem = m - j0;
+    if (m_rem <= CL * RT * RPT) {
+        // smallest cluster that gives every row a register slot: short panels keep to one or two SMs
+        int ncl = 1;
+        while (ncl * RT * RPT < m_rem) ncl *= 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(ncl, 1, 1);
+        cfg.blockDim = dim3(RT, 1, 1);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = ncl;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        TN_CUDA(cudaLaunchKernelEx(&cfg, qr_panel_reg_kernel, A, lda, m, j0, jb, Vall, ldv, T));
     } else {
+        const int rows_per = ceil_div(m_rem, CL);
         size_t smem = (size_t)rows_per * JB * sizeof(double);
         if (smem > 150 * 1024) {
             tn_set_error("QR panel of %d rows is too tall for the cluster panel kernels", m - j0);
@@ -441,6 +459,115 @@ int launch_panel(tn_ctx* ctx, cudaStream_t st, double* A, int lda, int m, int j0
         TN_CUDA(cudaFuncSetAttribute(qr_panel_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024));
         qr_panel_smem_kernel<<<CL, PT, smem, st>>>(A, lda, m, j0, jb, Vall, ldv, T);
     }
+    TN_LAUNCHED(ctx);
+    return TN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Block reflector of ONE inner panel applied to the other columns of its outer block:
+//   C2 <- (I - V T^T V^T) C2,   V (mr x kb, kb <= 16), C2 (mr x nc, nc <= 112).
+// As library GEMMs this is W = V^T C2 (split-K + reduction), W2 = T^T W, C2 -= V W2: four launches of ~15 us each for a
+// few MFLOP.  Here: (1) wy_w_kernel -- the whole grid streams V and C2 once, every CTA reduces its row chunk to a
+// 16 x 32 partial, and the LAST CTA to finish a column group (ticket counter) sums the partials in a fixed order and
+// multiplies by T^T; (2) wy_update_kernel -- C2 -= V W2 with W2's column in registers.  Two launches, ~10 us.
+constexpr int WY_COLS = 32;        // columns of C2 per CTA
+constexpr int WY_SL = 8;           // row slices per CTA (one warp each)
+constexpr size_t WY_SCRATCH = (size_t)(256 + 1) * JB * NB;      // partials of up to 256 row splits + W2, nc <= NB
+
+__global__ void __launch_bounds__(WY_COLS * WY_SL)
+wy_w_kernel(int mr, int kb, int nc, const double* __restrict__ V, int ldv, const double* __restrict__ T, int ldt,
+            const double* __restrict__ C2, int ldc, int rows_per_split, double* __restrict__ Wpart, int ncpad,
+            unsigned int* __restrict__ counters, double* __restrict__ W2) {
+    __shared__ double red[WY_SL][JB][WY_COLS + 1];
+    __shared__ double wfull[JB][WY_COLS + 1];
+    __shared__ int is_last;
+    const int c = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int col = blockIdx.x * WY_COLS + c;
+    const int split = blockIdx.y, S = gridDim.y;
+    const int r0 = split * rows_per_split, r1 = min(mr, r0 + rows_per_split);
+    double acc[JB];
+#pragma unroll
+    for (int k = 0; k < JB; ++k) acc[k] = 0.0;
+    for (int i = r0 + sl; i < r1; i += WY_SL) {
+        const double x = (col < nc) ? C2[(int64_t)i * ldc + col] : 0.0;
+        const double* v = V + (int64_t)i * ldv;            // the same row for the whole warp: broadcast loads
+#pragma unroll
+        for (int k = 0; k < JB; ++k) acc[k] += ((k < kb) ? v[k] : 0.0) * x;
+    }
+#pragma unroll
+    for (int k = 0; k < JB; ++k) red[sl][k][c] = acc[k];
+    __syncthreads();
+    for (int o = threadIdx.x; o < JB * WY_COLS; o += WY_COLS * WY_SL) {
+        const int k = o / WY_COLS, cc = o % WY_COLS;
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < WY_SL; ++q) s += red[q][k][cc];
+        Wpart[((int64_t)split * JB + k) * ncpad + blockIdx.x * WY_COLS + cc] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(&counters[blockIdx.x], 1u) == (unsigned)(S - 1));
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int o = threadIdx.x; o < JB * WY_COLS; o += WY_COLS * WY_SL) {
+        const int k = o / WY_COLS, cc = o % WY_COLS;
+        double s = 0.0;
+        for (int q = 0; q < S; ++q) s += Wpart[((int64_t)q * JB + k) * ncpad + blockIdx.x * WY_COLS + cc];
+        wfull[k][cc] = s;
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < JB * WY_COLS; o += WY_COLS * WY_SL) {
+        const int j = o / WY_COLS, cc = o % WY_COLS;
+        double s = 0.0;
+        if (j < kb)
+            for (int k = 0; k <= j; ++k) s += T[k * ldt + j] * wfull[k][cc];      // (T^T W)[j] : T is upper triangular
+        W2[(int64_t)j * ncpad + blockIdx.x * WY_COLS + cc] = s;
+    }
+    if (threadIdx.x == 0) counters[blockIdx.x] = 0;          // ready for the next call on this stream
+}
+
+__global__ void __launch_bounds__(WY_COLS * WY_SL)
+wy_update_kernel(int mr, int kb, int nc, const double* __restrict__ V, int ldv, const double* __restrict__ W2, int ncpad,
+                 double* __restrict__ C2, int ldc, int rows_per_cta) {
+    const int c = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int col = blockIdx.x * WY_COLS + c;
+    double w[JB];
+#pragma unroll
+    for (int k = 0; k < JB; ++k) w[k] = (k < kb) ? W2[(int64_t)k * ncpad + col] : 0.0;      // padded columns hold zeros
+    const int r0 = blockIdx.y * rows_per_cta, r1 = min(mr, r0 + rows_per_cta);
+    for (int i = r0 + sl; i < r1; i += WY_SL) {
+        const double* v = V + (int64_t)i * ldv;
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < JB; ++k) s += ((k < kb) ? v[k] : 0.0) * w[k];
+        if (col < nc) C2[(int64_t)i * ldc + col] -= s;
+    }
+}
+
+// W / W2 scratch of the caller must hold (splits * JB + JB) * ncpad doubles
+int apply_panel(tn_ctx* ctx, cudaStream_t st, int mr, int kb, int nc, const double* V, int ldv, const double* T, int ldt,
+                double* C2, int ldc, double* scratch, size_t scratch_doubles) {
+    const int groups = ceil_div(nc, WY_COLS), ncpad = groups * WY_COLS;
+    int S = ceil_div(2 * ctx->sm_count, groups);
+    const int max_by_rows = ceil_div(mr, 2 * WY_SL);                 // at least two rows per warp
+    if (S > max_by_rows) S = max_by_rows;
+    if (S > 256) S = 256;
+    if (S < 1) S = 1;
+    const int rows_per_split = ceil_div(mr, S);
+    S = ceil_div(mr, rows_per_split);
+    if ((size_t)(S + 1) * JB * ncpad > scratch_doubles) {
+        tn_set_error("apply_panel: scratch too small");
+        return TN_ERR_ARG;
+    }
+    double* Wpart = scratch;
+    double* W2 = scratch + (size_t)S * JB * ncpad;
+    wy_w_kernel<<<dim3(groups, S), WY_COLS * WY_SL, 0, st>>>(mr, kb, nc, V, ldv, T, ldt, C2, ldc, rows_per_split, Wpart, ncpad,
+                                                            (unsigned int*)ctx->counters, W2);
+    TN_LAUNCHED(ctx);
+    const int rows_per_cta = 64;
+    wy_update_kernel<<<dim3(groups, ceil_div(mr, rows_per_cta)), WY_COLS * WY_SL, 0, st>>>(mr, kb, nc, V, ldv, W2, ncpad, C2, ldc,
+                                                                                          rows_per_cta);
     TN_LAUNCHED(ctx);
     return TN_OK;
 }
@@ -456,10 +583,17 @@ int apply_block(tn_ctx* ctx, cudaStream_t st, int mr, int kb, int nc, const doub
 
 }  // namespace
 
+static bool fused_apply() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("TN_QR_APPLY"); on = (e && e[0] == 'g') ? 0 : 1; }
+    return on == 1;
+}
+
 static size_t qr_scratch_need(int m, int n) {
     const int k = m < n ? m : n;
     const int nouter = ceil_div(k, NB), npan = ceil_div(k, JB), wcols = n > k ? n : k;
-    return ((size_t)m * k + (size_t)npan * JB * JB + (size_t)nouter * NB * NB + (size_t)NB * NB + 2 * (size_t)NB * wcols) * sizeof(double);
+    return ((size_t)m * k + (size_t)npan * JB * JB + (size_t)nouter * NB * NB + (size_t)NB * NB + 2 * (size_t)NB * wcols +
+            WY_SCRATCH) * sizeof(double);
 }
 
 static int qr_body(tn_ctx* ctx, cudaStream_t st, int m, int n, double* A, int lda, double* Q, int ldq, double* R, int ldr,
@@ -477,6 +611,7 @@ static int qr_body(tn_ctx* ctx, cudaStream_t st, int m, int n, double* A, int ld
     double* G = Tout + (size_t)nouter * NB * NB;
     double* W = G + (size_t)NB * NB;
     double* W2 = W + (size_t)NB * wcols;
+    double* WY = W2 + (size_t)NB * wcols;
     const size_t tsmem = ((size_t)NB * NB + (size_t)NB * JB) * sizeof(double);
     TN_CUDA(cudaFuncSetAttribute(build_outer_T_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
     int rc;
@@ -491,8 +626,15 @@ static int qr_body(tn_ctx* ctx, cudaStream_t st, int m, int n, double* A, int ld
             if ((rc = launch_panel(ctx, st, A, lda, m, jj, jb, Vall, k, Tp))) return rc;
             const int rem = J0 + nbw - (jj + jb);       // remaining columns of this outer block
             if (rem > 0) {
-                if ((rc = apply_block(ctx, st, m - jj, jb, rem, Vall + (size_t)jj * k + jj, k, Tp, JB, 1,
-                                      A + (size_t)jj * lda + jj + jb, lda, W, W2))) return rc;
+                // two fused kernels on the FP64 vector pipe (fewer launches: better when many instances share the GPU) or
+                // three DMMA GEMMs + split-K reduction (shorter when the factorisation runs alone); TN_QR_APPLY=gemm|fused
+                if (fused_apply()) {
+                    if ((rc = apply_panel(ctx, st, m - jj, jb, rem, Vall + (size_t)jj * k + jj, k, Tp, JB,
+                                          A + (size_t)jj * lda + jj + jb, lda, WY, WY_SCRATCH))) return rc;
+                } else {
+                    if ((rc = apply_block(ctx, st, m - jj, jb, rem, Vall + (size_t)jj * k + jj, k, Tp, JB, 1,
+                                          A + (size_t)jj * lda + jj + jb, lda, W, W2))) return rc;
+                }
             }
         }
         double* To = Tout + (size_t)ob * NB * NB;

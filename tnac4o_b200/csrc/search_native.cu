@@ -142,6 +142,11 @@ extern "C" int tn_search_ground_state(tn_ctx* ctx, void* stream, int Nx, int Ny,
         for (int nx = Nx - 1; nx >= 1; --nx) {
             const tn_site* s = &sites[ny * Nx + nx];
             TRY(RRat[nx].alloc((size_t)nb0 * Drow[nx] * s->nl * 8, st));
+            // per branch-level 2 Dr nr Dl nl flop, plus the once-per-level A x Wtr contraction
+            tn_prof_scope prof(ctx, st, TN_P_RR,
+                               2.0 * nb0 * Drow[nx + 1] * s->nr * Drow[nx] * s->nl +
+                                   2.0 * s->nu * Drow[nx + 1] * s->nr * Drow[nx] * s->nl * s->nd,
+                               8.0 * nb0 * ((double)Drow[nx + 1] * s->nr + (double)Drow[nx] * s->nl));
             TRY(tn_rr_level(ctx, st, s, nb0, Drow[nx], Drow[nx + 1], Arow[nx], RRat[nx + 1].as<double>(),
                             br->vind.as<uint8_t>() + nx + 1, vs, RRat[nx].as<double>()));
         }
@@ -155,6 +160,12 @@ extern "C" int tn_search_ground_state(tn_ctx* ctx, void* stream, int Nx, int Ny,
             const tn_site* s = &sites[ny * Nx + nx];
             const int Dl = Drow[nx], Dr = Drow[nx + 1], B = br->n;
             // ---- marginals: T1 = RL . A on the DMMA path, then the fused kernel (tnac4o.py:1786-1807, 450-453)
+            // structure-aware work per branch marginal: 2 Dl nd Dr + 2 nd Dr nr + 4 nS flop and
+            // 8 (Dl + Dr nr + 2 nS) + 40 bytes
+            {
+            tn_prof_scope pm(ctx, st, TN_P_MARGINALS,
+                             (double)B * (2.0 * Dl * s->nd * Dr + 2.0 * s->nd * Dr * s->nr + 4.0 * s->nS),
+                             (double)B * (8.0 * (Dl + (double)Dr * s->nr + 2.0 * s->nS) + 40.0));
             TRY(tn_gemm_impl(ctx, st, 0, 0, B, s->nd * Dr, Dl, 1.0, br->RL.as<double>(), Dl, 0, Arow[nx], s->nd * Dr, 0, 0.0,
                              T1.as<double>(), s->nd * Dr, 0, 1));
             TRY(tn_marginals(ctx, st, s, B, Dr, T1.as<double>(), RRat[nx + 1].as<double>(), br->root.as<int32_t>(),
@@ -162,7 +173,10 @@ extern "C" int tn_search_ground_state(tn_ctx* ctx, void* stream, int Nx, int Ny,
                              d_maxbits, nullptr));
             min_flag_kernel<<<1, 256, 0, st>>>(flag.as<double>(), B, d_gmin);
             TN_LAUNCHED(ctx);
+            }
             marginals += B;
+            // selection / merge / top-M / materialise: 8 B per candidate read + ~48 B per survivor record
+            tn_prof_scope psel(ctx, st, TN_P_SELECT_MERGE, 0.0, 8.0 * B * s->nS);
             // ---- select -> expand -> merge -> top-M -> materialise (tnac4o.py:456-535)
             int K = 0, G = 0;
             TRY(tn_select(ctx, st, cand.as<double>(), (int64_t)B * s->nS, d_maxbits, relative_P_cutoff, surv.as<int32_t>(),

@@ -153,10 +153,13 @@ jacobi_round_kernel(double* __restrict__ E, int ldw, int a, int nc, int bsz, int
                     app += u * u; aqq += v * v; apq += u * v;
                 }
                 app = warp_sum(app); aqq = warp_sum(aqq); apq = warp_sum(apq);
-                if (fabs(apq) > tol * sqrt(app) * sqrt(aqq) && app > floor2 && aqq > floor2) {
-                    double zeta = (aqq - app) / (2.0 * apq);
-                    double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                    double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+                if (app > floor2 && aqq > floor2 && apq * apq > tol * tol * app * aqq) {
+                    // rotation of the smaller angle from two reciprocal square roots (see jacobi_cluster_kernel)
+                    const double d = aqq - app, h = 2.0 * apq;
+                    const double rr = rsqrt(d * d + h * h);
+                    const double x = 0.5 + 0.5 * (fabs(d) * rr);
+                    const double y = rsqrt(x);
+                    const double cs = x * y, sn = 0.5 * (copysign(1.0, d) * h * rr) * y;
                     for (int e = lane; e < ldw; e += 32) {
                         double u = xp[e], v = xq[e];
                         xp[e] = cs * u - sn * v;
@@ -260,14 +263,27 @@ jacobi_cluster_kernel(double* __restrict__ E, int ldw, int a, int ext, int nc, i
             {
                 int i = tid * ncl + rank;                          // pairs owned by this CTA: i % ncl == rank
                 if (tid < CJ_MAXOWN && i < half) {
+                    // partial sums added pairwise (a three-level tree for 8 CTAs): the FP64 pipe of this part is slow,
+                    // so the length of the dependent chain is what costs
                     double app = 0.0, aqq = 0.0, apq = 0.0;
-                    for (int src = 0; src < ncl; ++src) { app += part[src][tid][0]; aqq += part[src][tid][1]; apq += part[src][tid][2]; }
+                    for (int src = 0; src < ncl; src += 4) {
+                        const double a0 = part[src][tid][0] + part[src + 1][tid][0], a1 = part[src + 2][tid][0] + part[src + 3][tid][0];
+                        const double b0 = part[src][tid][1] + part[src + 1][tid][1], b1 = part[src + 2][tid][1] + part[src + 3][tid][1];
+                        const double c0 = part[src][tid][2] + part[src + 1][tid][2], c1 = part[src + 2][tid][2] + part[src + 3][tid][2];
+                        app += a0 + a1; aqq += b0 + b1; apq += c0 + c1;
+                    }
                     double cs = 1.0, sn = 0.0;
-                    if (fabs(apq) > tol * sqrt(app) * sqrt(aqq) && app > floor2 && aqq > floor2) {
-                        double zeta = (aqq - app) / (2.0 * apq);
-                        double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                        cs = 1.0 / sqrt(1.0 + t * t);
-                        sn = cs * t;
+                    if (app > floor2 && aqq > floor2 && apq * apq > tol * tol * app * aqq) {
+                        // Jacobi rotation of the smaller angle from two reciprocal square roots (no division):
+                        //   cos 2t = |d| / sqrt(d^2 + h^2),  sin 2t = sgn(d) h / sqrt(d^2 + h^2),   d = aqq - app, h = 2 apq
+                        //   cos t = sqrt((1 + cos 2t) / 2) = x rsqrt(x),   sin t = sin 2t / (2 cos t) = sin 2t rsqrt(x) / 2
+                        // identical in exact arithmetic to t = sgn(z) / (|z| + sqrt(1 + z^2)), z = d / h (the textbook form)
+                        const double d = aqq - app, h = 2.0 * apq;
+                        const double r = rsqrt(d * d + h * h);
+                        const double x = 0.5 + 0.5 * (fabs(d) * r);
+                        const double y = rsqrt(x);
+                        cs = x * y;
+                        sn = 0.5 * (copysign(1.0, d) * h * r) * y;
                         atomicAdd(&myrot, 1u);
                     }
                     for (int dstc = 0; dstc < ncl; ++dstc) {
@@ -462,9 +478,12 @@ jacobi_cluster2_kernel(double* __restrict__ E, int ldw, int a, int ext, int nc, 
                     apq += __shfl_xor_sync(0xffffffffu, apq, o);
                 }
                 if (valid && app > floor2 && aqq > floor2 && apq * apq > tol2 * app * aqq) {
-                    const double zeta = (aqq - app) / (2.0 * apq);
-                    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                    const double cs = rsqrt(1.0 + t * t), sn = cs * t;
+                    // rotation of the smaller angle from two reciprocal square roots (see jacobi_cluster_kernel)
+                    const double d = aqq - app, h = 2.0 * apq;
+                    const double rr = rsqrt(d * d + h * h);
+                    const double x = 0.5 + 0.5 * (fabs(d) * rr);
+                    const double y = rsqrt(x);
+                    const double cs = x * y, sn = 0.5 * (copysign(1.0, d) * h * rr) * y;
                     for (int e = sub; e < ll; e += 8) {
                         const double u = xp[e], v = xq[e];
                         xp[e] = cs * u - sn * v;
@@ -637,8 +656,11 @@ extern "C" int tn_svd(tn_ctx* ctx, void* stream, int m, int n, const double* C, 
     auto fit2 = [&](int nvec, int e) -> int {
         if (nvec < 2 || v1_only) return 0;
         const int halfp = (nvec + 1) / 2;
-        for (int ncl = 1; ncl <= CLJ_MAX; ncl *= 2) {
-            if (ncl == CLJ_MAX && !(wide_clusters() && wide_launchable())) break;
+        // measured on B200 (profiles/r2a_*): the non-tensor FP64 pipe issues ~15 FMA per clock and SM, so the redundant
+        // per-pair scalar work of this kernel only pays off while there is no cluster traffic at all (one CTA, <= 64
+        // vectors); larger problems use the owner-computes cluster kernel above
+        if (nvec > 64) return 0;
+        for (int ncl = 1; ncl <= 1; ncl *= 2) {
             size_t ll = ((size_t)ceil_div(a, ncl) + (size_t)ceil_div(e, ncl)) | 1;
             size_t bytes = (size_t)nvec * ll * sizeof(double) + (ncl > 1 ? (size_t)2 * ncl * halfp * 3 * sizeof(double) : 0);
             if (bytes <= CL_SMEM) return ncl;

@@ -187,6 +187,9 @@ class StreamPool:
                 while True:
                     item = self._q.get()
                     if item is None:
+                        from ._native import Context
+                        stream.synchronize()
+                        Context.release_thread()        # the thread's library contexts (scratch, pinned buffer, pool)
                         return
                     job, slot, results, errors, done = item
                     try:

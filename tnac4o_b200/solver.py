@@ -349,6 +349,19 @@ class tnac4o:
         self._sites = None
         self._host = None
 
+    def _check_limits(self, M, Dmax):
+        """limits of the device path that the reference API does not have, checked up front"""
+        if self.Nx > 63:
+            raise ValueError('Nx = %d: the packed boundary key holds at most 64 positions (Nx <= 63)' % self.Nx)
+        if Dmax > 256:
+            raise ValueError('Dmax = %d: left environments are materialised for bond dimensions up to 256' % Dmax)
+        if int(M) * int(np.max(self.N)) >= 2 ** 31:
+            raise ValueError('M x (states per cell) = %d x %d exceeds the 32-bit candidate index' % (M, int(np.max(self.N))))
+        if int(M) > 65535 * 64:
+            raise ValueError('M = %d: the grouped GEMM of the right environments places row tiles in gridDim.z (M <= 4 193 280)' % M)
+        for ny in range(self.Ny):
+            self._key_offsets(ny, self.Nx - 1)          # raises when a boundary row needs more than 128 bits
+
     # ------------------------------------------------------------------ search machinery
     def _key_offsets(self, ny, nx):
         """bit offsets of the Nx+1 boundary indices inside the 128-bit merge key after site (ny, nx)"""
@@ -489,6 +502,8 @@ class tnac4o:
         check(lib.tn_select(c.handle, c.stream, ptr(ws['cand']), ncand, ptr(ws['maxbits']), float(relative_P_cutoff),
                             ptr(ws['surv']), ptr(ws['count']), ptr(ws['pdbits']), ctypes.byref(K)))
         K = K.value
+        if K < 1:
+            raise RuntimeError('no candidate survived the cut-off at site (%d, %d): all marginals are NaN' % (ny, nx))
         offs = self._key_offsets(ny, nx)
         check(lib.tn_expand(c.handle, c.stream, site.ref, K, nx, int(nx > 0), int(ny > 0), self.Nx + 1,
                             offs.ctypes.data_as(ctypes.c_void_p), ptr(ws['surv']), ptr(br.vind), br.vind.stride(0),
@@ -503,7 +518,7 @@ class tnac4o:
         groups = None
         if ws.get('want_groups'):
             # member lists in sorted order are needed by the droplet pass before the key arrays are reused
-            groups = {'order': (ws['ktie'][:K] & 0xFFFFFFFF).to(torch.int32).cpu().numpy(), 'K': K, 'G': G}
+            groups = {'order': (ws['ktie'][:K] & 0xFFFFFFFF).to(torch.int32), 'K': K, 'G': G}
         check(lib.tn_topm(c.handle, c.stream, G, M, ptr(ws['g_prob']), ptr(ws['khi']), ptr(ws['klo']), ptr(ws['ktie']),
                           ptr(ws['sel']), ptr(ws['pdbits'])))
         Bn = min(G, M)
@@ -599,6 +614,7 @@ class tnac4o:
             shards = None
         if shards is not None:
             shards.bytes_gathered = 0
+        self._check_limits(M, Dmax)
         dev = self._dev()
         c = Context.get(dev)
         t0 = time.time()
@@ -644,6 +660,7 @@ class tnac4o:
         from .parallel import UniformStream
         stream = UniformStream(M, *(shard or (0, 1)))
         M = stream.hi - stream.lo
+        self._check_limits(M, Dmax)
         dev = self._dev()
         c = Context.get(dev)
         t0 = time.time()
@@ -706,6 +723,7 @@ class tnac4o:
         self.excitations_encoding = excitations_encoding
         if shards is not None and shards.world == 1:
             shards = None
+        self._check_limits(M, Dmax)
         dev = self._dev()
         c = Context.get(dev)
         t0 = time.time()
@@ -723,6 +741,8 @@ class tnac4o:
         ws['gmin'] = torch.ones(1, dtype=F64, device=dev)
         self._exc_initialise()
         book = None
+        if excitations_encoding == 1:
+            self._book_open(M)
         if excitations_encoding > 1:
             from .droplets import AdjacencyDroplets
             book = AdjacencyDroplets(excitations_encoding, self.mode)
@@ -742,7 +762,6 @@ class tnac4o:
                 groups = self._site_step(ws, RRat, ny, nx, M, relative_P_cutoff, min_dEng)
                 if book is None:
                     self._record_droplets(ws, old, groups, ny * self.Nx + nx, nsites, max_dEng, lim_hd)
-                    self._exc_clear_d()
                 else:
                     book.site_update(*self._merged_branches(ws, old, groups, ny * self.Nx + nx, nsites, max_dEng),
                                      max_dEng, lim_hd)
@@ -762,7 +781,7 @@ class tnac4o:
                 book.set_adjacency(self.J0, [self.ind0[ny][nx] for ny in range(self.Ny_model) for nx in range(self.Nx_model)])
             self.adj = book.adj
             return self.energy
-        self.el = self.el[0]
+        self._book_close()
         for key, (dpos, dstate) in self.d.items():
             dpos = self.order_i[dpos]
             srt = dpos.argsort()
@@ -776,7 +795,7 @@ class tnac4o:
         dev = self._dev()
         c = Context.get(dev)
         K, G = groups['K'], groups['G']
-        order = groups['order']
+        order = groups['order'].cpu().numpy()
         Bn = ws['cur'].n
         host = lambda t, n: t[:n].cpu().numpy()
         g_rep, g_start, g_size = host(ws['g_rep'], G), host(ws['g_start'], G), host(ws['g_size'], G)
@@ -810,56 +829,63 @@ class tnac4o:
         return [int(parent[g_rep[g]]) for g in sel], merged
 
     def _record_droplets(self, ws, old, groups, last, nsites, max_dEng, lim_hd):
-        """excitation lists of the new branches (tnac4o.py:844-882).  The XOR differences between the winner and the
-        merged-away members are produced by one integer kernel launch per site (tn_xor_diff); dictionary and tree
-        stay host objects in the reference's own format (they are what save() writes)."""
-        dev = self._dev()
-        c = Context.get(dev)
-        K, G = groups['K'], groups['G']
-        order = groups['order']
+        """excitation lists of the new branches (tnac4o.py:844-882) on the device (csrc/droplet_book.cu): pairs of winner and
+        merged-away member, their XOR differences, the dictionary of droplet shapes, the new tree nodes with their pruned
+        sub-excitations and the per-branch lists are all produced by integer kernels from the arrays the merge left in
+        HBM; only two counters per site come back to the host"""
+        c = Context.get(self._dev())
+        K = groups['K']
         Bn = ws['cur'].n
-        host = lambda t, n: t[:n].cpu().numpy()
-        g_rep, g_start, g_size = host(ws['g_rep'], G), host(ws['g_start'], G), host(ws['g_size'], G)
-        g_E, g_prob = host(ws['g_E'], G), host(ws['g_prob'], G)
-        sel = host(ws['sel'], Bn)
-        Enew, Pnew = host(ws['Enew'], K), host(ws['Pnew'], K)
-        parent, cell = host(ws['parent'], K), host(ws['cell'], K)
-        # pairs (winner, member) that become droplets
-        pw, pm, pg = [], [], []
-        for j, g in enumerate(sel):
-            if g_size[g] > 1:
-                members = order[g_start[g]:g_start[g] + g_size[g]]
-                gap = Enew[members] - g_E[g]
-                for m in members[(gap <= max_dEng) & (members != g_rep[g])]:
-                    pw.append(g_rep[g]); pm.append(m); pg.append(j)
-        diffs = {}
-        if pw:
-            npairs = len(pw)
-            i32 = lambda a: torch.as_tensor(np.asarray(a, dtype=np.int32), device=dev)
-            row_a, row_b = i32(parent[pw]), i32(parent[pm])
-            cell_a, cell_b = i32(cell[pw]), i32(cell[pm])
-            out_pos = torch.empty((npairs, nsites), dtype=torch.int16, device=dev)
-            out_xor = torch.empty((npairs, nsites), dtype=torch.uint8, device=dev)
-            out_len = torch.empty(npairs, dtype=torch.int32, device=dev)
-            check(lib.tn_xor_diff(c.handle, c.stream, npairs, nsites, last, ptr(old.states), ptr(row_a), ptr(cell_a),
-                                  ptr(row_b), ptr(cell_b), ptr(out_pos), ptr(out_xor), ptr(out_len)))
-            out_pos, out_xor, out_len = out_pos.cpu().numpy(), out_xor.cpu().numpy().view(np.int8), out_len.cpu().numpy()
-            for k in range(npairs):
-                diffs.setdefault(pg[k], []).append((pm[k], out_pos[k, :out_len[k]].astype(np.int64), out_xor[k, :out_len[k]].copy()))
-        new_el = []
-        for j, g in enumerate(sel):
-            winner = g_rep[g]
-            bel = self.el[parent[winner]][:]
-            for m, dpos, dstate in diffs.get(j, []):
-                gap = Enew[m] - g_E[g]
-                if (lim_hd <= 1) or (self._exc_hd(dstate) >= lim_hd):
-                    dfirst = dpos[0]
-                    di = self._exc_add_to_d(dpos, dstate)
-                    sel_sub = [self._exc_cut_energy(sne, max_dEng - (sne[0][0] + gap)) for sne in self.el[parent[m]]
-                               if (sne[0][3] >= dfirst) and (sne[0][0] + gap <= max_dEng)]
-                    bel.append(((gap, di, dfirst, last, Pnew[m] - g_prob[g]), tuple(sel_sub)))
-            new_el.append(bel)
-        self.el = new_el
+        check(lib.tn_book_site(c.handle, self._book, int(last), int(K), int(Bn), ptr(groups['order']), ptr(ws['g_rep']),
+                               ptr(ws['g_start']), ptr(ws['g_size']), ptr(ws['g_E']), ptr(ws['g_prob']), ptr(ws['sel']),
+                               ptr(ws['Enew']), ptr(ws['Pnew']), ptr(ws['parent']), ptr(ws['cell']), ptr(old.states),
+                               float(max_dEng), int(lim_hd) if self.mode == 'Ising' else -int(lim_hd)))
+
+    def _book_open(self, M):
+        c = Context.get(self._dev())
+        handle = ctypes.c_void_p()
+        check(lib.tn_book_create(c.handle, c.stream, self.Nx * self.Ny, int(M), ctypes.byref(handle)))
+        self._book = handle
+
+    def _book_close(self):
+        """pools -> the reference's host structures: el (nested tuples of branch 0, pruned with the budgets the device kept
+        lazily: _exc_cut_energy, tnac4o.py:2071-2079), d / invd / free_d (shapes the tree references)"""
+        c = Context.get(self._dev())
+        sizes = (ctypes.c_int64 * 6)()
+        check(lib.tn_book_sizes(c.handle, self._book, sizes))
+        nn, nc, nsh, nel, n0, npairs = (int(x) for x in sizes)
+        f8 = lambda n: np.zeros(max(n, 1), dtype=np.float64)
+        i4 = lambda n: np.zeros(max(n, 1), dtype=np.int32)
+        dE, dP, key, first, last, cptr, ccnt = f8(nn), f8(nn), i4(nn), i4(nn), i4(nn), i4(nn), i4(nn)
+        cnode, cbud = i4(nc), f8(nc)
+        sptr, spos, sxor = i4(nsh + 1), np.zeros(max(nel, 1), dtype=np.int16), np.zeros(max(nel, 1), dtype=np.uint8)
+        list0 = i4(n0)
+        hp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        check(lib.tn_book_export(c.handle, self._book, hp(dE), hp(dP), hp(key), hp(first), hp(last), hp(cptr), hp(ccnt),
+                                 hp(cnode), hp(cbud), hp(sptr), hp(spos), hp(sxor), hp(list0)))
+        lib.tn_book_free(self._book)
+        self._book = None
+        self.stats['droplet_pairs'] = npairs
+        self.stats['droplet_nodes'] = nn
+        used = set()
+
+        def build(n, budget):
+            used.add(int(key[n]))
+            kids = []
+            for e in range(cptr[n], cptr[n] + ccnt[n]):
+                ch = cnode[e]
+                if dE[ch] <= budget:
+                    kids.append(build(ch, min(cbud[e], budget - dE[ch])))
+            return ((dE[n], int(key[n]), int(first[n]), int(last[n]), dP[n]), tuple(kids))
+
+        self.el = [build(int(n), np.inf) for n in list0[:n0]]
+        self.d, self.invd = {}, {}
+        for k in sorted(used):
+            dpos = spos[sptr[k]:sptr[k + 1]].astype(np.int64)
+            dstate = sxor[sptr[k]:sptr[k + 1]].view(np.int8).copy()
+            self.d[k] = (dpos, dstate)
+            self.invd.setdefault(self._exc_get_sh((dpos, dstate)), []).append(k)
+        self.free_d = nsh
 
     # ---- droplet dictionary / tree (host objects in the reference's save format; tnac4o.py:2012-2079, 2249-2285)
     def _exc_initialise(self):
@@ -869,41 +895,11 @@ class tnac4o:
     def _exc_get_sh(exc):
         return (exc[0][0], exc[1][0], exc[0][-1], exc[1][-1])
 
-    def _exc_add_to_d(self, dpos, dstate):
-        sh = self._exc_get_sh((dpos, dstate))
-        for k in self.invd.get(sh, []):
-            if np.array_equal(dpos, self.d[k][0]) and np.array_equal(dstate, self.d[k][1]):
-                return k
-        k = self.free_d
-        self.invd.setdefault(sh, []).append(k)
-        self.d[k] = (dpos, dstate)
-        self.free_d += 1
-        return k
-
-    def _exc_cut_energy(self, exc, maxdE):
-        return (exc[0], tuple(self._exc_cut_energy(se, maxdE - se[0][0]) for se in exc[1] if se[0][0] <= maxdE))
-
     def _exc_hd(self, dstate):
         """tnac4o.py:2143-2150"""
         if self.mode == 'RMF':
             return sum(bin(int(st)).count('1') for st in dstate)
         return len(dstate)
-
-    def _exc_get_unique_keys(self, excs):
-        out = set()
-        for e in excs:
-            out.add(e[0][1])
-            out |= self._exc_get_unique_keys(e[1])
-        return out
-
-    def _exc_clear_d(self):
-        live = set()
-        for bel in self.el:
-            live |= self._exc_get_unique_keys(bel)
-        self.d = {k: self.d[k] for k in live}
-        self.invd = {}
-        for k in live:
-            self.invd.setdefault(self._exc_get_sh(self.d[k]), []).append(k)
 
     def _adjacency_book(self):
         """droplet structure of encodings 2 / 3 around the solver's (or a loaded file's) d / el / adj"""

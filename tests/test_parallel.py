@@ -85,8 +85,24 @@ def _shard_worker(rank, world, port, out):
         gmin = torch.tensor([full[lo:hi].min() if hi > lo else 1.0], dtype=torch.float64)
         sh.allreduce_min_(gmin)
         cnt = sh.allreduce_sum_(torch.tensor([float(hi - lo)], dtype=torch.float64))
+        # survivors-only exchange of the sharded selection (solver._select_sharded): every rank keeps the candidates of its
+        # slice above a common threshold; counts, padded ids and padded values are all-gathered
+        thr = full.max() - 1.0
+        flat = full.reshape(-1)
+        mine = np.nonzero(flat[lo * 256:hi * 256] > thr)[0] + lo * 256
+        counts = sh.allgather_small(torch.tensor([len(mine)], dtype=torch.int64)).tolist()
+        kmax = max(counts)
+        ids = torch.zeros(kmax, dtype=torch.int32)
+        vals = torch.zeros(kmax, dtype=torch.float64)
+        ids[:len(mine)] = torch.from_numpy(mine.astype(np.int32))
+        vals[:len(mine)] = torch.from_numpy(flat[mine])
+        all_i, all_v = sh.allgather_small(ids).view(world, kmax), sh.allgather_small(vals).view(world, kmax)
+        got_i = np.concatenate([all_i[r, :n].numpy() for r, n in enumerate(counts)])
+        got_v = np.concatenate([all_v[r, :n].numpy() for r, n in enumerate(counts)])
+        want = np.nonzero(flat > thr)[0]
+        surv_ok = np.array_equal(np.sort(got_i), want) and np.array_equal(got_v, flat[got_i])
         res.append((B, np.array_equal(buf[:B].numpy(), full), int(bits.item()) == int(ordered(full.max())[0]),
-                    float(gmin.item()) == min(full.min(), 1.0), cnt.item() == B))
+                    float(gmin.item()) == min(full.min(), 1.0), cnt.item() == B, surv_ok))
     t = torch.arange(6, dtype=torch.float64) * (rank + 1)
     sh.broadcast_(t, src=0)
     same = (sh.same_everywhere([(1, 2), (3,)]), sh.same_everywhere(rank))

@@ -133,16 +133,66 @@ def test_marginals_end_to_end_against_reference_trace(J128):
 
 
 def test_config2_L512(J128):
+    """BASELINE config 2 against the reference fixture AND, site by site, against the oracle's trace of every conditional
+    marginal: max |dP| <= 1e-8 on the normalised 256-vectors (measured 2.6e-9, tests/tools/parity_probe.py), accumulated
+    log2 P to 1e-10 relative (measured 1.5e-13)"""
+    from oracle import RefSolver
     z = golden('ref_l512.npz')
-    ins = make(droplet_couplings(512), L=512)
+    J = droplet_couplings(512)
+    ref = make(J, L=512, cls=RefSolver)
+    trace = {}
+    ref.trace = lambda kind, **kw: trace.setdefault((kind, kw['ny'], kw['nx']), kw)
+    ref.search_ground_state(M=2 ** 10, relative_P_cutoff=1e-8, Dmax=16)
+    ins = make(J, L=512)
+    ins.native_search = False          # the spy below hooks the Python site loop
+    seen = {}
+    orig = ins._site_marginals
+
+    def spy(ws, br, RRat, ny, nx, want_P=False):
+        P = orig(ws, br, RRat, ny, nx, want_P=True)
+        seen[(ny, nx)] = (P.cpu().numpy(), br.vind[:br.n].cpu().numpy().copy())
+        return None
+    ins._site_marginals = spy
     ins.search_ground_state(M=2 ** 10, relative_P_cutoff=1e-8, Dmax=16)
+    worst = 0.0
+    assert len(seen) == 64
+    for (ny, nx), (P, vind) in seen.items():
+        r = trace[('marginals', ny, nx)]
+        rows = {tuple(v): i for i, v in enumerate(r['vind'].view(np.uint8).tolist())}
+        common = [(i, rows[tuple(v)]) for i, v in enumerate(vind.tolist()) if tuple(v) in rows]
+        assert len(common) >= 0.9 * len(rows)                               # borderline members of the top-M cut may differ
+        a, b = zip(*common)
+        worst = max(worst, np.max(np.abs(P[list(a)] - r['P'][list(b)])))
+    assert worst <= 1e-8
+    assert ins.energy[0] == ref.energy[0] and np.array_equal(ins.states, ref.states)
     assert abs(ins.energy[0] - z['gs_energy'][0]) < 1e-9
     assert np.array_equal(ins.states, z['gs_states'])
     e_file, bits_file = droplet_golden(512, 1)
     assert abs(ins.energy[0] - e_file) < 1e-5 and np.array_equal(ins.binary_states()[0], bits_file)
-    # L=2048 truncations are ill-conditioned: the reference against itself (gesdd vs gesvd, or two CPUs) moves rhoT by
-    # 1 - fidelity ~ 4e-12 and the accumulated log2 P by ~1e-6 relative
-    np.testing.assert_allclose(ins.probability, z['gs_probability'], rtol=5e-6)
+    np.testing.assert_allclose(ins.probability, z['gs_probability'], rtol=1e-10)
+    np.testing.assert_allclose(ins.probability, ref.probability, rtol=1e-10)
+    # native driver = the instrumented Python loop
+    nat = make(J, L=512)
+    nat.search_ground_state(M=2 ** 10, relative_P_cutoff=1e-8, Dmax=16)
+    assert np.array_equal(nat.energy, ins.energy) and np.array_equal(nat.states, ins.states)
+    assert np.array_equal(nat.probability, ins.probability)
+
+
+def test_synthetic_family_A_instance_against_oracle():
+    """the kind of instance that fills the bench batches (file values permuted over the same coupling pattern,
+    SURVEY.md section 8d family A) at L=512: energy and state bit-exact, log2 P to 1e-10 against the oracle"""
+    from oracle import RefSolver
+    J = droplet_couplings(512)
+    rng = np.random.default_rng(7)
+    vals = np.array([v for _, _, v in J])
+    Js = [[i, j, float(v)] for (i, j, _), v in zip(J, rng.permutation(vals))]
+    ref = make(Js, L=512, cls=RefSolver)
+    ref.search_ground_state(M=2 ** 10, relative_P_cutoff=1e-8, Dmax=16)
+    ins = make(Js, L=512)
+    ins.search_ground_state(M=2 ** 10, relative_P_cutoff=1e-8, Dmax=16)
+    assert ins.energy[0] == ref.energy[0] and np.array_equal(ins.states, ref.states)
+    assert int(ins.degeneracy) == int(ref.degeneracy)
+    np.testing.assert_allclose(ins.probability, ref.probability, rtol=1e-10)
 
 
 def test_gibbs_sampling(J128):
@@ -154,9 +204,8 @@ def test_gibbs_sampling(J128):
     assert ins.states.shape == (128, 16)
     E = tnac4o_b200.energy_Jij(J128, ins.binary_states())
     assert np.max(np.abs(E - ins.energy)) < 1e-6                            # examples/test_examples.py:56
-    same = np.all(ins.states == z['gibbs_states'], axis=1)
-    assert same.mean() >= 0.98                                              # identical draws up to 1e-9-level CDF ties
-    assert np.max(np.abs(ins.energy[same] - z['gibbs_energy'][same])) < 1e-10
+    assert np.array_equal(ins.states, z['gibbs_states'])                    # same uniforms => the same 128 samples
+    assert np.max(np.abs(ins.energy - z['gibbs_energy'])) < 1e-10
 
 
 @pytest.mark.parametrize('rot', [0, 1])
@@ -186,9 +235,15 @@ def test_config4_L2048_M1024():
     e_file, bits_file = droplet_golden(2048, 1)
     assert abs(ins.energy[0] - e_file) < 1e-5
     bits = ins.binary_states()[0]
-    # the ground state is two-fold degenerate: accept either member, check its energy exactly
+    # The ground state is two-fold degenerate: the two members differ in 3 spins and have the SAME
+    # float64 energy here and in the reference (E diff 0.0, tests/tools/parity_probe.py).  Which one survives is decided
+    # where the two branches merge: the reference takes np.argmin over the group in the order its unstable argsort left
+    # them (tnac4o.py:482, 497), this package the first minimum in the total order of the candidate ids.  At M = 2^10 the
+    # reference returns one member, this package the other (the one groundstates_otn2d.txt lists, which the reference
+    # itself returns at M = 2^12 -- test below, where the states are identical); either is accepted here, the energy
+    # is exact and the degeneracy is counted.
     d_ref, d_file = int(np.sum(bits != z['gs_bits'][0])), int(np.sum(bits != bits_file))
-    assert min(d_ref, d_file) == 0, (d_ref, d_file)
+    assert min(d_ref, d_file) == 0 and max(d_ref, d_file) == 3, (d_ref, d_file)
     E = tnac4o_b200.energy_Jij(J, ins.binary_states())
     assert abs(E[0] - ins.energy[0]) < 1e-6
     # L=2048 truncations are ill-conditioned: the reference against itself (gesdd vs gesvd, or two CPUs) moves rhoT by
@@ -207,7 +262,7 @@ def test_config4_L2048_M4096():
     assert int(ins.degeneracy) == int(z['gs_degeneracy']) == 2
     bits = ins.binary_states()[0]
     e_file, bits_file = droplet_golden(2048, 1)
-    assert min(int(np.sum(bits != z['gs_bits'][0])), int(np.sum(bits != bits_file))) == 0
+    assert np.array_equal(bits, z['gs_bits'][0]) and np.array_equal(bits, bits_file)      # the reference's state, bit for bit
     assert abs(tnac4o_b200.energy_Jij(J, ins.binary_states())[0] - ins.energy[0]) < 1e-6
     np.testing.assert_allclose(ins.probability, z['gs_probability'], rtol=5e-6)
     assert abs(ins.discarded_probability - float(z['gs_discarded'])) < 1e-3
@@ -224,9 +279,8 @@ def test_config5_gibbs_L2048_against_reference_samples():
     ins = make(J, L=2048, beta=1)
     np.random.seed(1)
     ins.gibbs_sampling(M=256, Dmax=32)
-    same = np.all(ins.states == z['states'], axis=1)
-    assert same.mean() >= 0.98                               # identical draws up to 1e-9-level CDF ties
-    assert np.max(np.abs(ins.energy[same] - z['energy'][same])) < 1e-9
+    assert np.array_equal(ins.states, z['states'])           # all 256 samples identical, state by state
+    assert np.max(np.abs(ins.energy - z['energy'])) < 1e-9
     assert ins.negative_probability >= float(z['negative']) - 1e-9
 
 

@@ -16,7 +16,7 @@
 
 namespace {
 
-constexpr int TBM = 128, TBN = 128, TBK = 16, TST = 4;
+constexpr int TBM = 128, TBN = 128, TBK = 16, TST = 6;
 constexpr int TWM = 32, TWN = 64;
 constexpr int A_BYTES = TBM * TBK * 8;            // 16 KiB
 constexpr int B_SUB_BYTES = TBK * 16 * 8;         // one 16 (k) x 16 (n) box: 2 KiB
@@ -88,6 +88,19 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+    // Swizzled fragment addresses, hoisted out of the k loop.  128-byte swizzle: the 16-byte chunk index of an element is
+    // XORed with (row & 7) of its 128-byte row.
+    //   A tile [128 rows m][16 k]: element (r, k), r = wm*32 + i*8 + g, k = kk + t  ->  r*128 + (((k>>1) ^ g) << 4) + (k&1)*8;
+    //     (k>>1) ^ g = ((kk/2) ^ (g&6)) | ((t>>1) ^ (g&1)): one thread-constant per kk, the i-dependence is the immediate i*1024.
+    //   B tile: eight [16 rows k][16 n] boxes; element (k, n), n = wn*64 + j*8 + g  ->
+    //     (n>>4)*2048 + k*128 + ((((n&15)>>1) ^ (k&7)) << 4) + (n&1)*8,  ((n&15)>>1) ^ (k&7) = (((j&1)*4) ^ (kk&4)) | ((g>>1) ^ t):
+    //     the (j, kk) part is a compile-time constant, the rest one thread-constant.
+    const int baseA = (wm * TWM + g) * 128 + ((((t >> 1) ^ (g & 1))) << 4) + ((t & 1) << 3);
+    int xa[TBK / 4];
+#pragma unroll
+    for (int q = 0; q < TBK / 4; ++q) xa[q] = ((2 * q) ^ (g & 6)) << 4;
+    const int baseB = wn * (TWN / 16) * B_SUB_BYTES + t * 128 + ((((g >> 1) ^ t)) << 4) + ((g & 1) << 3);
+
     for (int kt = 0; kt < ktiles; ++kt) {
         const int st = kt % TST;
         const unsigned parity = (unsigned)((kt / TST) & 1);
@@ -97,29 +110,24 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (++spins > (1u << 28)) __trap();          // a lost transaction must fail the launch, not hang the GPU
             }
         }
-        const unsigned char* sa = base + (size_t)st * STAGE_BYTES;
-        const unsigned char* sb = sa + A_BYTES;
+        // every warp has finished tile kt - 1: its stage is refilled (tile kt - 1 + TST) while tile kt is multiplied
+        __syncthreads();
+        if (tid == 0 && kt >= 1 && kt - 1 + TST < ktiles) issue((kt - 1) % TST, kt - 1 + TST);
+        const unsigned char* sa = base + (size_t)st * STAGE_BYTES + baseA;
+        const unsigned char* sb = base + (size_t)st * STAGE_BYTES + A_BYTES + baseB;
 #pragma unroll
         for (int kk = 0; kk < TBK; kk += 4) {
-            const int k = kk + t;
             double fa[TM], fb[TN];
 #pragma unroll
-            for (int i = 0; i < TM; ++i) {
-                const int r = wm * TWM + i * 8 + g;
-                fa[i] = *(const double*)(sa + r * 128 + ((((k >> 1) ^ (r & 7))) << 4) + ((k & 1) << 3));
-            }
+            for (int i = 0; i < TM; ++i) fa[i] = *(const double*)(sa + xa[kk >> 2] + i * 1024);
 #pragma unroll
-            for (int j = 0; j < TN; ++j) {
-                const int n = wn * TWN + j * 8 + g;
-                fb[j] = *(const double*)(sb + (n >> 4) * B_SUB_BYTES + k * 128 + (((((n & 15) >> 1) ^ (k & 7))) << 4) + ((n & 1) << 3));
-            }
+            for (int j = 0; j < TN; ++j)
+                fb[j] = *(const double*)(sb + (j >> 1) * B_SUB_BYTES + kk * 128 + (((((j & 1) << 2) ^ (kk & 4))) << 4));
 #pragma unroll
             for (int i = 0; i < TM; ++i)
 #pragma unroll
                 for (int j = 0; j < TN; ++j) dmma(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
         }
-        __syncthreads();                                     // every warp is done with stage st
-        if (tid == 0 && kt + TST < ktiles) issue(st, kt + TST);
     }
 
 #pragma unroll

@@ -83,8 +83,9 @@ qr_panel_reg_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, doub
 
     // The register file of every thread is ROTATED by one column per step, so the current column is always slot 0,
     // the columns still to be updated are slots 1 .. 15-j and the finished reflectors are slots 16-j .. 15.  The loop
-    // body is therefore the same code for every column (a fully unrolled version is 160 KB of SASS and runs out of
-    // the instruction cache).
+    // body is therefore the same code for every column.  (Measured in round 2: a fully unrolled variant with
+    // compile-time column indices -- no rotation, no per-element predicates, 2.3x fewer instructions per column -- is
+    // 330 KB of SASS and 2-12 % SLOWER: 4461 vs 4359 us for 8192 x 512, profiles/r2b_time_qr_lean_vs_rotating.txt.)
     PH_DECL
     PH(0);
 #pragma unroll 1

@@ -25,6 +25,9 @@ namespace cg = cooperative_groups;
 
 namespace {
 
+// x mod n for 0 <= x < 2n without an integer division (the tournament indices are computed per pair and per phase)
+__device__ __forceinline__ int wrap(int x, int n) { return x >= n ? x - n : x; }
+
 constexpr int JT = 512;              // threads per CTA
 constexpr int JW = JT / 32;
 constexpr size_t SMEM_LIMIT = 200 * 1024;
@@ -141,8 +144,8 @@ jacobi_round_kernel(double* __restrict__ E, int ldw, int a, int nc, int bsz, int
         unsigned int my_rot = 0;
         for (int r = 0; r < (nce > 1 ? r1 : 0); ++r) {
             for (int i = warp; i < half; i += JW) {
-                int p = (r + i) % r1;
-                int q = (i == 0) ? r1 : (r + r1 - i) % r1;
+                int p = wrap(r + i, r1);
+                int q = (i == 0) ? r1 : wrap(r + r1 - i, r1);
                 if (p >= ncol || q >= ncol) continue;
                 if (p > q) { int t = p; p = q; q = t; }
                 double* xp = S + (int64_t)p * ldw;
@@ -203,6 +206,7 @@ jacobi_cluster_kernel(double* __restrict__ E, int ldw, int a, int ext, int nc, i
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int ncl = (int)cluster.num_blocks();        // 8 or 16 (launch attribute)
+    const int ncl_log2 = (ncl == 16) ? 4 : 3;
     extern __shared__ __align__(16) double Sl[];      // [nc][ll]
     __shared__ double part[CLJ_MAX][CJ_MAXOWN][3];
     __shared__ double rot[CJ_MAXPAIRS][2];
@@ -235,8 +239,8 @@ jacobi_cluster_kernel(double* __restrict__ E, int ldw, int a, int ext, int nc, i
                 int p = 0, q = 0;
                 bool valid = (i < half);
                 if (valid) {
-                    p = (r + i) % r1;
-                    q = (i == 0) ? r1 : (r + r1 - i) % r1;
+                    p = wrap(r + i, r1);
+                    q = (i == 0) ? r1 : wrap(r + r1 - i, r1);
                     valid = (p < nc) && (q < nc);
                 }
                 if (valid) {
@@ -254,7 +258,7 @@ jacobi_cluster_kernel(double* __restrict__ E, int ldw, int a, int ext, int nc, i
                     apq += __shfl_xor_sync(0xffffffffu, apq, o);
                 }
                 if (sub == 0 && i < half) {
-                    double* dst = cluster.map_shared_rank(&part[rank][i / ncl][0], i % ncl);
+                    double* dst = cluster.map_shared_rank(&part[rank][i >> ncl_log2][0], i & (ncl - 1));
                     dst[0] = app; dst[1] = aqq; dst[2] = apq;
                 }
             }
@@ -299,8 +303,8 @@ jacobi_cluster_kernel(double* __restrict__ E, int ldw, int a, int ext, int nc, i
                 if (i >= half) continue;
                 const double cs = rot[i][0], sn = rot[i][1];
                 if (sn == 0.0) continue;
-                int p = (r + i) % r1;
-                int q = (i == 0) ? r1 : (r + r1 - i) % r1;
+                int p = wrap(r + i, r1);
+                int q = (i == 0) ? r1 : wrap(r + r1 - i, r1);
                 double* xp = Sl + (int64_t)p * lls;
                 double* xq = Sl + (int64_t)q * lls;
                 if (!vglob) {
@@ -417,8 +421,8 @@ jacobi_cluster2_kernel(double* __restrict__ E, int ldw, int a, int ext, int nc, 
                     bool valid = (i < half);
                     int p = 0, q = 0;
                     if (valid) {
-                        p = (r + i) % r1;
-                        q = (i == 0) ? r1 : (r + r1 - i) % r1;
+                        p = wrap(r + i, r1);
+                        q = (i == 0) ? r1 : wrap(r + r1 - i, r1);
                         valid = (p < nc) && (q < nc);
                     }
                     double app = 0.0, aqq = 0.0, apq = 0.0;
@@ -451,8 +455,8 @@ jacobi_cluster2_kernel(double* __restrict__ E, int ldw, int a, int ext, int nc, 
                 bool valid = (i < half);
                 int p = 0, q = 0;
                 if (valid) {
-                    p = (r + i) % r1;
-                    q = (i == 0) ? r1 : (r + r1 - i) % r1;
+                    p = wrap(r + i, r1);
+                    q = (i == 0) ? r1 : wrap(r + r1 - i, r1);
                     valid = (p < nc) && (q < nc);
                 }
                 double* xp = Sl + (int64_t)p * lls;

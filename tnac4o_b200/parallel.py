@@ -111,6 +111,17 @@ class BranchShards:
             dist.all_gather_into_tensor(full, mine.clone(), group=self.group)
         return buf
 
+    def allgather_small(self, t):
+        """all-gather of a small 1-d tensor (same length on every rank) -> 1-d tensor of world * len, rank-major"""
+        self.bytes_gathered += t.numel() * t.element_size() * self.world
+        if self.host and t.is_cuda:
+            out = torch.empty(self.world * t.numel(), dtype=t.dtype)
+            dist.all_gather_into_tensor(out, t.cpu().contiguous(), group=self.group)
+            return out.to(t.device)
+        out = torch.empty(self.world * t.numel(), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        return out
+
     def _allreduce(self, t, op):
         if self.host and t.is_cuda:
             h = t.cpu()

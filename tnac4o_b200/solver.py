@@ -419,28 +419,23 @@ class tnac4o:
 
     def _setup_RR(self, br, ny, shards=None):
         """right environments of row ny for every row-start branch, all levels (tnac4o.py:1768-1784).
-        RRat[nx] covers sites nx..Nx-1; site nx of the search uses RRat[nx + 1].  With ``shards`` every rank
-        contracts the levels of its own slice of branches and the levels are all-gathered at the end of the row
-        set-up (a branch met later in the row may descend from any row-start branch)."""
+        RRat[nx] covers sites nx..Nx-1; site nx of the search uses RRat[nx + 1].  With ``shards`` the environments are
+        REPLICATED: every rank contracts all row-start branches (67 MFLOP per level plus 0.5 MFLOP per branch on the DMMA
+        path -- cheaper than exchanging 16 MB per level, and a branch met later in the row may descend from any of them)."""
         dev = self._dev()
         c = Context.get(dev)
         sites = self._site_tables()[ny]
         A = self.rhoT[ny + 1].A
         nb = br.n
-        lo, hi, rows = (0, nb, nb) if shards is None else (*shards.slice(nb), shards.padded(nb))
         RRat = [None] * (self.Nx + 1)
-        RRat[self.Nx] = torch.ones((rows, 1, 1), dtype=F64, device=dev)
+        RRat[self.Nx] = torch.ones((nb, 1, 1), dtype=F64, device=dev)
         for nx in range(self.Nx - 1, 0, -1):
             Dl, nd, Dr = A[nx].shape
-            out = torch.empty((rows, Dl, sites[nx].nl), dtype=F64, device=dev)
-            if hi > lo:
-                up = br.vind[lo:, nx + 1:]
-                check(lib.tn_rr_level(c.handle, c.stream, sites[nx].ref, hi - lo, Dl, Dr, ptr(A[nx]), ptr(RRat[nx + 1][lo:]),
-                                      up.data_ptr(), br.vind.stride(0), ptr(out[lo:])))
+            out = torch.empty((nb, Dl, sites[nx].nl), dtype=F64, device=dev)
+            up = br.vind[:, nx + 1:]
+            check(lib.tn_rr_level(c.handle, c.stream, sites[nx].ref, nb, Dl, Dr, ptr(A[nx]), ptr(RRat[nx + 1]),
+                                  up.data_ptr(), br.vind.stride(0), ptr(out)))
             RRat[nx] = out
-        if shards is not None:
-            for nx in range(self.Nx - 1, 0, -1):
-                shards.allgather_rows(RRat[nx], nb)
         br.root[:nb] = torch.arange(nb, dtype=torch.int32, device=dev)
         return RRat
 
@@ -466,9 +461,9 @@ class tnac4o:
         return P
 
     def _site_marginals_sharded(self, ws, br, RRat, site, A, nx, shards):
-        """the same kernels on this rank's slice [lo, hi) of the branches, then the exchange step of the site
-        (SURVEY.md section 8e): all-gather of the candidate log-probabilities cand[b][s] and max over ranks of the
-        best candidate, after which every rank holds what the single-GPU path holds at this point."""
+        """the same kernels on this rank's slice [lo, hi) of the branches, then the first half of the site's exchange step
+        (SURVEY.md section 8e): the best candidate log-probability over all ranks (8-byte max-reduce).  The candidates
+        themselves stay where they were computed; _select_sharded exchanges only those that survive the cut-off."""
         c = Context.get(self._dev())
         Dl, nd, Dr = A.shape
         B = br.n
@@ -482,11 +477,38 @@ class tnac4o:
             ws['gmin'] = torch.minimum(ws['gmin'], ws['flag'][lo:hi].min())
         else:
             ws['maxbits'].zero_()                      # the smallest ordered encoding: this rank contributes nothing
-        rows = shards.padded(B)
-        shards.allgather_rows(ws['cand'][:rows * nS].view(rows, nS), B)
         shards.allreduce_max_ordered_(ws['maxbits'])
         self.stats['marginals'] = self.stats.get('marginals', 0) + (hi - lo)
         return None
+
+    def _select_sharded(self, ws, B, nS, relative_P_cutoff, shards):
+        """second half of the exchange step: every rank applies the relative cut-off (tnac4o.py:456-465) to ITS slice of the
+        candidates, then the survivors -- (candidate id, log-probability), 12 bytes each, typically 10^3-10^4 of the
+        B x 256 candidates -- are all-gathered, so that every rank holds the survivor list and their values the
+        single-GPU path holds at this point.  Returns the number of survivors."""
+        dev = self._dev()
+        c = Context.get(dev)
+        lo, hi = shards.slice(B)
+        K = ctypes.c_int(0)
+        if hi > lo:
+            check(lib.tn_select(c.handle, c.stream, ptr(ws['cand'][lo * nS:]), (hi - lo) * nS, ptr(ws['maxbits']),
+                                float(relative_P_cutoff), ptr(ws['surv']), ptr(ws['count']), ptr(ws['pdbits']), ctypes.byref(K)))
+        k_loc = K.value
+        ids = ws['surv'][:k_loc] + lo * nS                                   # global candidate ids of my survivors
+        vals = ws['cand'][ids.long()]
+        counts = shards.allgather_small(torch.tensor([k_loc], dtype=torch.int64, device=dev)).tolist()
+        kmax = max(counts)
+        pad_i = torch.zeros(kmax, dtype=torch.int32, device=dev)
+        pad_v = torch.zeros(kmax, dtype=F64, device=dev)
+        pad_i[:k_loc], pad_v[:k_loc] = ids, vals
+        all_i = shards.allgather_small(pad_i).view(shards.world, kmax)
+        all_v = shards.allgather_small(pad_v).view(shards.world, kmax)
+        keep = torch.cat([all_i[r, :n] for r, n in enumerate(counts)])
+        kept_v = torch.cat([all_v[r, :n] for r, n in enumerate(counts)])
+        Ktot = int(keep.numel())
+        ws['surv'][:Ktot] = keep
+        ws['cand'][keep.long()] = kept_v                                     # expand reads cand[id] of every survivor
+        return Ktot
 
     def _site_step(self, ws, RRat, ny, nx, M, relative_P_cutoff, min_dEng):
         """one site of the branch-and-bound: select -> expand -> merge -> top-M -> materialise (tnac4o.py:456-535)"""
@@ -498,10 +520,13 @@ class tnac4o:
         Dl, nd, Dr = A.shape
         B = br.n
         ncand = B * site.nS
-        K = ctypes.c_int(0)
-        check(lib.tn_select(c.handle, c.stream, ptr(ws['cand']), ncand, ptr(ws['maxbits']), float(relative_P_cutoff),
-                            ptr(ws['surv']), ptr(ws['count']), ptr(ws['pdbits']), ctypes.byref(K)))
-        K = K.value
+        if ws.get('shards') is not None:
+            K = self._select_sharded(ws, B, site.nS, relative_P_cutoff, ws['shards'])
+        else:
+            K = ctypes.c_int(0)
+            check(lib.tn_select(c.handle, c.stream, ptr(ws['cand']), ncand, ptr(ws['maxbits']), float(relative_P_cutoff),
+                                ptr(ws['surv']), ptr(ws['count']), ptr(ws['pdbits']), ctypes.byref(K)))
+            K = K.value
         if K < 1:
             raise RuntimeError('no candidate survived the cut-off at site (%d, %d): all marginals are NaN' % (ny, nx))
         offs = self._key_offsets(ny, nx)
@@ -541,6 +566,7 @@ class tnac4o:
         shards = ws.get('shards')
         if shards is not None:
             shards.allreduce_min_(ws['gmin'])
+            shards.allreduce_max_ordered_(ws['pdbits'])          # largest discarded log-probability over all slices
             self.stats['marginals_this_rank'] = self.stats.get('marginals', 0)
             tot = torch.tensor([float(self.stats.get('marginals', 0))], dtype=F64, device=self._dev())
             self.stats['marginals'] = int(shards.allreduce_sum_(tot).item())

@@ -39,12 +39,12 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 CFG = dict(L=2048, Nx=16, Ny=16, Nc=8, beta=3.0, M=2 ** 10, Dmax=32, relative_P_cutoff=1e-8)
 METRIC = 'L=2048 chimera ground-state search, seconds per instance'
 UNIT = 's/instance'
-# dram__bytes_read.sum + dram__bytes_write.sum of one gemm_kernel<128,128,32,64> launch (the 8192 x 512 x 512 attach
-# GEMM), from the ncu --set full capture summarised in profiles/r1a_ncu_full_prof_gemm.csv
-NCU_TRAFFIC_LARGE_GEMM = {'bytes': 35968256,
-                          'note': 'per launch of the 8192x512x512 attach GEMM (ncu --set full, profiles/r1a_ncu_full_prof_gemm.csv): '
-                                  '35.7 MB read + 0.27 MB written to DRAM against 69 MB algorithmic operand bytes -- the 33.5 MB '
-                                  'result stays in the 126 MB L2 for its consumer; `achieved` is summed over all GEMM launches of the step'}
+NCU_TRAFFIC_LARGE_GEMM = {'bytes': 35686912 + 315136,
+                          'note': 'dram__bytes_read.sum + dram__bytes_write.sum of one gemm_tma_kernel launch (the 8192x512x512 attach GEMM) '
+                                  'from this round\'s ncu --set full capture of this build (profiles/r2b_ncu_summary.txt): 35.7 MB read + '
+                                  '0.3 MB written against 69 MB algorithmic operand + result bytes -- the 33.5 MB result stays in the '
+                                  '126 MB L2 for its consumer.  A profiler cannot run inside the timed region; the other primitives of the '
+                                  'roofline move < 2 MB per launch (QR panel: 1.1 MB read, Jacobi: 4.2 MB)'}
 
 
 def instance_couplings(rank):
@@ -171,6 +171,34 @@ def extra_configs(torch, dist, tnac4o_b200, parallel, dev, rank, world):
                             'seconds_total': t, 'seconds_rhoT_replicated': gib.stats['seconds_rhoT'], 'seconds_sampling': s_samp,
                             'samples_per_s': M5 / s_samp, 'branch_marginals_per_s': M5 * CFG['Nx'] * CFG['Ny'] / s_samp,
                             'mean_energy': float(np.mean(E)), 'samples_gathered': int(len(E))}
+    # config 3: low-energy spectrum of L=1152 #1 (ee=1, dE=1, Dmax=32) and its decode; one rank (the search is not sharded
+    # here), the others wait at the next barrier
+    if rank == 0:
+        import time as _t
+        from conftest import droplet_couplings, golden
+        sp = tnac4o_b200.tnac4o(mode='Ising', Nx=12, Ny=12, Nc=8, J=droplet_couplings(1152), beta=CFG['beta'], device=dev)
+        torch.cuda.synchronize(dev)
+        t0 = _t.perf_counter()
+        sp.search_low_energy_spectrum(excitations_encoding=1, M=1024, relative_P_cutoff=CFG['relative_P_cutoff'], Dmax=CFG['Dmax'],
+                                      max_dEng=1.0)
+        torch.cuda.synchronize(dev)
+        t_search = _t.perf_counter() - t0
+        pairs, nodes = sp.stats.get('droplet_pairs'), sp.stats.get('droplet_nodes')
+        sp.decode_low_energy_states(max_dEng=1.0, max_states=2 ** 20)          # warm-up of the decode buffers
+        sp2 = tnac4o_b200.tnac4o(mode='Ising', Nx=12, Ny=12, Nc=8, J=droplet_couplings(1152), beta=CFG['beta'], device=dev)
+        sp2.excitations_encoding, sp2.d, sp2.invd, sp2.el, sp2.free_d = 1, sp.d, sp.invd, sp.el, sp.free_d
+        sp2.energy, sp2.states = sp.energy[:1].copy(), sp.states[:1].copy()      # sorted ascending: entry 0 is the ground state
+        t0 = _t.perf_counter()
+        sp2.decode_low_energy_states(max_dEng=1.0, max_states=2 ** 20)
+        t_decode = _t.perf_counter() - t0
+        z = golden('ref_l1152.npz')
+        out['config3_spectrum'] = {'workload': 'e03 + e04: low-energy spectrum L=1152 #1 (ee=1, dE=1, M=2^10, Dmax=32) and decode, one GPU',
+                                   'seconds_search': t_search, 'seconds_decode': t_decode, 'decoded_states': int(len(sp2.energy)),
+                                   'decoded_states_per_s': len(sp2.energy) / t_decode, 'droplet_pairs': pairs, 'tree_nodes_created': nodes,
+                                   'droplet_shapes': len(sp.d),
+                                   'reference_seconds_search_build_container': float(z['seconds_search']),
+                                   'reference_seconds_decode_build_container': float(z['seconds_decode']),
+                                   'reference_decoded_states': int(z['n_states'])}
     return out
 
 
@@ -271,7 +299,9 @@ def run_gpu(args):
     total_e2e = time.perf_counter() - t_begin
     h2d = B * ins._host_tables().nbytes
     d2h = B * (ins.energy.nbytes + ins.states.nbytes + ins.probability.nbytes + 3 * 8)
-    # single-instance latency (one stream), two extra steps outside the timed region
+    # single-instance latency (one stream), two extra steps outside the timed region; the host spins while it waits here
+    # (a sleeping thread adds ~0.4 ms per read-back, 0.7 s per instance, which only matters when nothing else runs)
+    _check(_lib.tn_set_blocking_sync(0))
     lat_runs = [step(False, [ins]) for _ in range(2)]
     lat = min(r[0] for r in lat_runs)
     lat_stats = lat_runs[-1][2]
@@ -319,6 +349,7 @@ def run_gpu(args):
                                '(tn_profile: CUDA events on the launching stream around every primitive call)'}
 
     roofline = roofline_pass() if rank == 0 else None      # before the one-off heavy runs below: same thermal state as the timed region
+    _check(_lib.tn_set_blocking_sync(1))
     # ---- BASELINE configs 4 and 5 as quoted (outside the timed region): ONE search at M = 2^12 with its branch batch
     # sharded over all ranks (NCCL all-gather of the candidate log-probabilities per site), and
     # 10^5 Gibbs samples at beta = 1 sharded over the ranks (no collective until the final gather)
@@ -539,7 +570,7 @@ if __name__ == '__main__':
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--batch', type=int, default=12, help='independent instances solved concurrently per GPU')
+    ap.add_argument('--batch', type=int, default=24, help='independent instances solved concurrently per GPU')
     ap.add_argument('--no-extra', action='store_true', help='skip the one-off runs of configs 4 (M=2^12) and 5 (Gibbs)')
     a = ap.parse_args()
     if a.impl == 'reference':

@@ -219,6 +219,100 @@ marginals_kernel(int nb, int nS, int nl, int nd, int nr, int nu, int Dr, const d
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same marginals with ONE WARP per branch and the (d x Dr) . (Dr x r) product on the DMMA path, for the interior
+// chimera shape nd = nr = 16 (every site that is not on the right / bottom edge).  The one-CTA-per-branch kernel above
+// spends its time in four block-wide reductions and recomputes w[s] * t2[d(s), r(s)] three times (13 % of the HBM peak at
+// 10^5 branches, profiles/r1c_*); here a warp loads its branch's T1 and RR fragments straight from global memory (each
+// element exactly once: 8 KB per branch), accumulates the 16 x 16 result in four m8n8k4 tiles, parks it in 2 KB of
+// shared memory for the indirect look-up t2[d(s), r(s)], keeps its 8 of the 256 state weights in registers, and reduces
+// min / sum / max with warp shuffles.  No block barrier; a branch's result does not depend on its neighbours in the
+// launch (the sharded search relies on that).
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+constexpr int MW_WARPS = 8;
+
+__global__ void __launch_bounds__(MW_WARPS * 32)
+marginals_warp_kernel(int nb, int nS, int nu, int Dr, const double* __restrict__ Wlu, const uint8_t* __restrict__ dmap,
+                      const uint8_t* __restrict__ rmap, const double* __restrict__ T1, const double* __restrict__ RR,
+                      const int32_t* __restrict__ root, const uint8_t* __restrict__ vind, int vstride, int nx,
+                      const double* __restrict__ prob, double* __restrict__ cand, double* __restrict__ flag,
+                      unsigned long long* max_bits, double* __restrict__ P_out) {
+    __shared__ double t2s[MW_WARPS][16 * 16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    double* t2 = t2s[warp];
+    double wmax = -INFINITY;
+    for (int b = blockIdx.x * MW_WARPS + warp; b < nb; b += gridDim.x * MW_WARPS) {
+        const double* t1 = T1 + (int64_t)b * 16 * Dr;
+        const double* rr = RR + (int64_t)root[b] * Dr * 16;
+        double acc[2][2][2] = {};
+        for (int kk = 0; kk < Dr; kk += 4) {
+            const double a0 = t1[(int64_t)g * Dr + kk + t], a1 = t1[(int64_t)(8 + g) * Dr + kk + t];
+            const double b0 = rr[(int64_t)(kk + t) * 16 + g], b1 = rr[(int64_t)(kk + t) * 16 + 8 + g];
+            dmma_m8n8k4(acc[0][0][0], acc[0][0][1], a0, b0);
+            dmma_m8n8k4(acc[0][1][0], acc[0][1][1], a0, b1);
+            dmma_m8n8k4(acc[1][0][0], acc[1][0][1], a1, b0);
+            dmma_m8n8k4(acc[1][1][0], acc[1][1][1], a1, b1);
+        }
+        __syncwarp();                                   // the previous branch's look-ups are done
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                t2[(i * 8 + g) * 16 + j * 8 + 2 * t] = acc[i][j][0];
+                t2[(i * 8 + g) * 16 + j * 8 + 2 * t + 1] = acc[i][j][1];
+            }
+        __syncwarp();
+        const int l = vind[(int64_t)b * vstride + nx], u = vind[(int64_t)b * vstride + nx + 1];
+        const double* w = Wlu + ((int64_t)l * nu + u) * nS;
+        double p[8];
+        double pmin = INFINITY;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int s = lane + 32 * q;
+            p[q] = (s < nS) ? w[s] * t2[dmap[s] * 16 + rmap[s]] : INFINITY;
+            pmin = fmin(pmin, p[q]);
+        }
+        pmin = warp_min(pmin);
+        double fl = pmin, cntneg = 0.0, tot = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (lane + 32 * q < nS) {
+                if (pmin < 0.0 && p[q] < fabs(pmin)) { p[q] = fabs(pmin); cntneg += 1.0; }
+                tot += p[q];
+            }
+        }
+        tot = warp_sum(tot);
+        if (pmin < 0.0) { cntneg = warp_sum(cntneg); fl = pmin * cntneg; }
+        double inv = 0.0;
+        if (tot > 0.0) { inv = 1.0 / tot; fl *= inv; } else fl = -1.0;
+        const double pb = prob ? prob[b] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int s = lane + 32 * q;
+            if (s < nS) {
+                const double pn = (tot > 0.0) ? p[q] * inv : p[q] + 1.0 / (double)nS;
+                if (P_out) P_out[(int64_t)b * nS + s] = pn;
+                if (cand) {
+                    const double c = log2(pn) + pb;
+                    cand[(int64_t)b * nS + s] = c;
+                    wmax = fmax(wmax, c);
+                }
+            }
+        }
+        if (lane == 0) flag[b] = fl;
+    }
+    if (cand && max_bits) {
+        wmax = warp_max(wmax);
+        if (lane == 0 && wmax > -INFINITY) atomicMax(max_bits, ordered_bits(wmax));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // relative cut-off (tnac4o.py:456-465): keep cand > max + log2cut; record the largest discarded value
 __global__ void select_kernel(const double* __restrict__ cand, int64_t n, const unsigned long long* max_bits, double log2cut,
                               int use_cut, int32_t* __restrict__ surv, int* count, unsigned long long* pd_bits) {
@@ -507,6 +601,16 @@ int tn_marginals(tn_ctx* ctx, void* stream, const tn_site* site, int nb, int Dr,
     if (nb == 0) return TN_OK;
     cudaStream_t st = as_stream(stream);
     if (max_bits) TN_CUDA(cudaMemsetAsync(max_bits, 0, sizeof(unsigned long long), st));
+    static const bool warp_path = [] { const char* e = getenv("TN_MARGINALS"); return !(e && e[0] == 'c'); }();
+    if (warp_path && site->nd == 16 && site->nr == 16 && site->nS <= 256 && Dr % 4 == 0) {
+        // interior chimera shape: one warp per branch, (d x Dr) . (Dr x r) on DMMA (TN_MARGINALS=cta selects the old kernel)
+        const int want = ceil_div(nb, MW_WARPS);
+        const int grid = want < 16 * ctx->sm_count ? want : 16 * ctx->sm_count;
+        marginals_warp_kernel<<<grid, MW_WARPS * 32, 0, st>>>(nb, site->nS, site->nu, Dr, site->Wlu, site->dmap, site->rmap, T1, RR,
+                                                             root, vind, vstride, nx, prob, cand, flag, max_bits, P_out);
+        TN_LAUNCHED(ctx);
+        return TN_OK;
+    }
     size_t smem = ((size_t)site->nd * Dr + (size_t)Dr * site->nr + (size_t)site->nd * site->nr) * sizeof(double);
     TN_REQUIRE(smem <= 220 * 1024, "bond dimension too large for marginals shared memory");
     TN_CUDA(cudaFuncSetAttribute(marginals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));

@@ -53,6 +53,9 @@ int tn_profile_read(tn_ctx* ctx, double* h_out, int ncat);
 /* cudaDeviceScheduleBlockingSync for the current device: waiting host threads sleep instead of spinning (the reference is
  * single-threaded; this is for running many solver instances per GPU from fewer host cores) */
 int tn_set_blocking_sync(int on);
+/* throughput mode (process-wide): kernels that can trade latency for SM occupancy do so -- the cluster Jacobi SVD uses 4
+ * instead of 8 CTAs when its vectors fit; for runs where many solver instances share one GPU (TN_THROUGHPUT=1 does the same) */
+int tn_set_throughput_mode(int on);
 
 /* ---------------------------------------------------------------- boundary-MPS primitives (tnac4o/mps.py) */
 

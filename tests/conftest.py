@@ -31,6 +31,20 @@ def droplet_golden(L, k=1):
     return float(z['gs_%d_%03d_energy' % (L, k)]), z['gs_%d_%03d_bits' % (L, k)]
 
 
+def droplet_couplings10(L, k):
+    """instances 001-010 of every size (instances10.npz stores 75 J as integers); identical floats to droplet_couplings"""
+    z = golden('instances10.npz')
+    dJ = float(1 / 75)
+    return [[int(a) - 1, int(b) - 1, int(c) * dJ] for a, b, c in zip(z['J_%d_%03d_i' % (L, k)], z['J_%d_%03d_j' % (L, k)],
+                                                                  z['J_%d_%03d_v75' % (L, k)])]
+
+
+def droplet_golden10(L, k):
+    z = golden('instances10.npz')
+    key = 'gs_%d_%03d_bits' % (L, k)
+    return float(z['gs_%d_%03d_energy' % (L, k)]), (z[key] if key in z.files else None)
+
+
 SHAPES = {128: (4, 4), 512: (8, 8), 1152: (12, 12), 2048: (16, 16)}
 
 

@@ -10,6 +10,7 @@ Runs only in the build container, where the reference is mounted read-only at
 Fixtures
   instances.npz       coupling lists of droplet instances 001-003 (L=128), 001 (L=512, 1152, 2048), J124 C8 #1,
                       with the matching lines of groundstates_otn2d.txt / results_*.txt
+  instances10.npz     droplet instances 001-010 of L = 128, 512, 1152, 2048 (couplings as 75 J, int16) + golden energies / states
   ref_small.npz       L=128 #1: search_ground_state / spectrum / Gibbs outputs for several (rot, precondition, D)
                       plus per-site traces (marginals of every branch, branch records after merge + top-M)
   ref_l512.npz        config 2: L=512 #1, M=2^10, Dmax=16
@@ -83,6 +84,25 @@ def make_instances():
     out['J124_C8_001_v'] = raw[:, 2].astype(np.float64)
     out['J124_C8_001_energy_deg'] = np.array([-2309, 1152], dtype=np.int64)    # results file / test_examples.py:142
     np.savez_compressed(os.path.join(HERE, 'instances.npz'), **out)
+
+
+def make_instances10():
+    """droplet instances 001-010 of every lattice size with their lines of groundstates_otn2d.txt (the
+    10-instance mean); couplings as 75 * J (odd integers, int16) to keep the file small"""
+    out = {}
+    for L in (128, 512, 1152, 2048):
+        for k in range(1, 11):
+            raw = raw_couplings(L, k)
+            out['J_%d_%03d_i' % (L, k)] = raw[:, 0].astype(np.int16)
+            out['J_%d_%03d_j' % (L, k)] = raw[:, 1].astype(np.int16)
+            v75 = np.round(raw[:, 2] * 75)
+            assert np.max(np.abs(v75 / 75 - raw[:, 2])) < 1e-5
+            out['J_%d_%03d_v75' % (L, k)] = v75.astype(np.int16)
+            e, bits = golden_line(L, k)
+            out['gs_%d_%03d_energy' % (L, k)] = np.float64(e)
+            if len(bits):
+                out['gs_%d_%03d_bits' % (L, k)] = bits
+    np.savez_compressed(os.path.join(HERE, 'instances10.npz'), **out)
 
 
 def result_fields(ins, tag, out):
@@ -353,7 +373,7 @@ def make_j124():
 if __name__ == '__main__':
     for what in sys.argv[1:]:
         t0 = time.time()
-        {'instances': make_instances, 'small': make_small,
+        {'instances': make_instances, 'instances10': make_instances10, 'small': make_small,
          'l512': lambda: make_big(512, 16, 1024, 'ref_l512.npz'),
          'l2048': lambda: make_big(2048, 32, 1024, 'ref_l2048.npz'),
          'l2048m4096': lambda: make_big(2048, 32, 4096, 'ref_l2048_m4096.npz'),

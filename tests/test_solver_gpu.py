@@ -422,3 +422,20 @@ def test_native_search_driver_equals_python_loop(J128):
         assert np.array_equal(a.probability, b.probability) and a.degeneracy == b.degeneracy
         assert a.discarded_probability == b.discarded_probability and a.negative_probability == b.negative_probability
         assert a.stats['marginals'] == b.stats['marginals']
+
+
+@pytest.mark.parametrize('L,D', [(128, 32), (512, 32)])
+def test_ten_instances_reach_the_golden_energies(L, D):
+    """droplet instances 001-010 against groundstates_otn2d.txt: energy to the file's print
+    precision, and the file's state wherever the ground state is not degenerate"""
+    import tnac4o_b200
+    from conftest import droplet_couplings10, droplet_golden10
+    for k in range(1, 11):
+        J = droplet_couplings10(L, k)
+        ins = make(J, L=L)
+        ins.search_ground_state(M=2 ** 10, relative_P_cutoff=1e-8, Dmax=D)
+        e_file, bits_file = droplet_golden10(L, k)
+        assert abs(ins.energy[0] - e_file) < 1e-5, (L, k, ins.energy[0], e_file)
+        assert abs(tnac4o_b200.energy_Jij(J, ins.binary_states()[:1])[0] - ins.energy[0]) < 1e-6
+        if int(ins.degeneracy) == 1:
+            assert np.array_equal(ins.binary_states()[0], bits_file), (L, k)

@@ -37,6 +37,7 @@ _SIGS = {
     'tn_profile': (c_int, [P, c_int]),
     'tn_profile_read': (c_int, [P, P, c_int]),
     'tn_set_blocking_sync': (c_int, [c_int]),
+    'tn_set_throughput_mode': (c_int, [c_int]),
     'tn_gemm': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_double, P, c_int, c_int64, P, c_int, c_int64,
                         c_double, P, c_int, c_int64, c_int]),
     'tn_transpose': (c_int, [P, P, c_int, c_int, P, c_int, P, c_int]),

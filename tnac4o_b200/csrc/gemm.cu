@@ -5,6 +5,8 @@
 // Replaces the np.tensordot -> dgemm calls of the reference's boundary-MPS code (mps.py:655-769) and of
 // tnac4o.py:1779-1794.  Row-major, arbitrary M, N, K and leading dimensions, strided batch, deterministic
 // split-K (partials in context scratch, reduced in a fixed order).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -179,8 +181,12 @@ int launch_cfg(tn_ctx* ctx, cudaStream_t st, int tA, int tB, int M, int N, int K
     }
     int tiles = ceil_div(M, BM) * ceil_div(N, BN) * batch;
     int splitk = 1;
-    if (tiles * 2 <= ctx->sm_count && K >= 512 && !bmap) {
-        splitk = min(min(ctx->sm_count / tiles, K / 256), 32);
+    static const int cta_cap = [] { const char* e = getenv("TN_GEMM_SPLITK_CTAS"); return e ? atoi(e) : 0; }();
+    // CTAs a split-K product may spread over: the whole GPU when it runs alone, a quarter of it in throughput mode
+    // (measured with 32 concurrent instances: 0.440 vs 0.476 s per instance, profiles/r2c_bench_batch_sweep.txt)
+    const int target = cta_cap > 0 ? cta_cap : (tn_throughput_mode() ? ctx->sm_count / 4 : ctx->sm_count);
+    if (tiles * 2 <= target && K >= 512 && !bmap) {
+        splitk = min(min(target / tiles, K / 256), 32);
         if (splitk < 1) splitk = 1;
     }
     int kchunk = ceil_div(ceil_div(K, splitk), BK) * BK;
@@ -216,6 +222,7 @@ int launch_cfg(tn_ctx* ctx, cudaStream_t st, int tA, int tB, int M, int N, int K
 
 }  // namespace
 
+int tn_throughput_mode();
 int tn_gemm_tma_try(tn_ctx* ctx, cudaStream_t st, int M, int N, int K, double alpha, const double* A, int lda, const double* B,
                     int ldb, double beta, double* C, int ldc);
 

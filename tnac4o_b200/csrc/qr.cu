@@ -20,6 +20,8 @@
 
 namespace cg = cooperative_groups;
 
+int tn_throughput_mode();      // svd.cu: many solver instances share the GPU -> small grids for the latency-bound helpers
+
 int tn_gemm_impl(tn_ctx* ctx, cudaStream_t st, int tA, int tB, int M, int N, int K, double alpha, const double* A,
                  int lda, int64_t sA, const double* B, int ldb, int64_t sB, double beta, double* C, int ldc, int64_t sC,
                  int batch);
@@ -550,7 +552,11 @@ wy_update_kernel(int mr, int kb, int nc, const double* __restrict__ V, int ldv, 
 int apply_panel(tn_ctx* ctx, cudaStream_t st, int mr, int kb, int nc, const double* V, int ldv, const double* T, int ldt,
                 double* C2, int ldc, double* scratch, size_t scratch_doubles) {
     const int groups = ceil_div(nc, WY_COLS), ncpad = groups * WY_COLS;
-    int S = ceil_div(2 * ctx->sm_count, groups);
+    // row splits: ~2 CTAs per SM when the factorisation runs alone; TN_WY_CTAS caps the grid (experiments with many
+    // concurrent instances)
+    static const int cta_cap = [] { const char* e = getenv("TN_WY_CTAS"); return e ? atoi(e) : 0; }();
+    const int want_ctas = cta_cap > 0 ? cta_cap : (tn_throughput_mode() ? ctx->sm_count / 2 : 2 * ctx->sm_count);
+    int S = ceil_div(want_ctas, groups);
     const int max_by_rows = ceil_div(mr, 2 * WY_SL);                 // at least two rows per warp
     if (S > max_by_rows) S = max_by_rows;
     if (S > 256) S = 256;

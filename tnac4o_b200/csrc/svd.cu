@@ -206,7 +206,7 @@ jacobi_cluster_kernel(double* __restrict__ E, int ldw, int a, int ext, int nc, i
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int ncl = (int)cluster.num_blocks();        // 8 or 16 (launch attribute)
-    const int ncl_log2 = (ncl == 16) ? 4 : 3;
+    const int ncl_log2 = (ncl == 16) ? 4 : (ncl == 8 ? 3 : 2);   // 4-CTA clusters: throughput mode (half the SMs per SVD)
     extern __shared__ __align__(16) double Sl[];      // [nc][ll]
     __shared__ double part[CLJ_MAX][CJ_MAXOWN][3];
     __shared__ double rot[CJ_MAXPAIRS][2];
@@ -590,6 +590,13 @@ __global__ void truncation_rank_kernel(const double* __restrict__ S, int k, doub
 
 }  // namespace
 
+static int g_throughput_mode = -1;
+int tn_throughput_mode() {
+    if (g_throughput_mode < 0) { const char* e = getenv("TN_THROUGHPUT"); g_throughput_mode = (e && e[0] == '1') ? 1 : 0; }
+    return g_throughput_mode;
+}
+extern "C" int tn_set_throughput_mode(int on) { g_throughput_mode = on ? 1 : 0; return TN_OK; }
+
 // 0 = portable 8-CTA clusters only, 1 = 16-CTA clusters where 8 do not fit (default), 2 = also prefer 16 CTAs for
 // every problem with >= 96 live vectors (environment TN_SVD_WIDE = 0 / 1 / 2, read once)
 static int wide_clusters() {
@@ -767,7 +774,11 @@ extern "C" int tn_svd(tn_ctx* ctx, void* stream, int m, int n, const double* C, 
         // 16 CTAs (non-portable cluster size) for larger problems; and when even that is too small for vectors plus
         // accumulated right vectors, 16 CTAs with only the w-parts resident and the right vectors rotated in L2
         const bool fits8 = cluster_fits(nc, ext), fits16 = wide_clusters() && wide_launchable() && cluster_fits(nc, ext, CLJ_MAX);
-        const int ncl = (fits8 && !(wide_clusters() == 2 && fits16 && nc >= 96)) ? CLJ : CLJ_MAX;
+        // Throughput mode (tn_set_throughput_mode, used when many solver instances share the GPU): a 4-CTA cluster when
+        // the vectors fit its shared memory and every CTA owns at most CJ_MAXOWN pairs -- ~1.3x the time on half the SMs,
+        // and at most two 8-CTA clusters fit one GPC anyway.
+        const bool fits4 = tn_throughput_mode() && cluster_fits(nc, ext, 4) && (nc + 1) / 2 <= 4 * CJ_MAXOWN;
+        const int ncl = fits4 ? 4 : ((fits8 && !(wide_clusters() == 2 && fits16 && nc >= 96)) ? CLJ : CLJ_MAX);
         const int vglob = (ncl == CLJ_MAX && !fits16) ? 1 : 0;
         size_t ll = ((size_t)ceil_div(a, ncl) + (vglob ? 0 : (size_t)ceil_div(ext, ncl))) | 1;
         size_t smem = (size_t)nc * ll * sizeof(double);

@@ -9,6 +9,8 @@
 
 #include "common.cuh"
 
+int tn_throughput_mode();      // svd.cu: many solver instances share the GPU
+
 namespace {
 
 constexpr int BK = 16;
@@ -222,7 +224,6 @@ int launch_cfg(tn_ctx* ctx, cudaStream_t st, int tA, int tB, int M, int N, int K
 
 }  // namespace
 
-int tn_throughput_mode();
 int tn_gemm_tma_try(tn_ctx* ctx, cudaStream_t st, int M, int N, int K, double alpha, const double* A, int lda, const double* B,
                     int ldb, double beta, double* C, int ldc);
 

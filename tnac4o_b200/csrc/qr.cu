@@ -11,8 +11,6 @@
 //     (V_outer, T_outer) is then applied to the trailing matrix and, at the end, to Q with K = 128 DMMA GEMMs.
 #include <cooperative_groups.h>
 
-#include <map>
-#include <mutex>
 #include <stdlib.h>
 #include <utility>
 
@@ -685,106 +683,15 @@ static int qr_body(tn_ctx* ctx, cudaStream_t st, int m, int n, double* A, int ld
     return TN_OK;
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// CUDA-graph replay.  One factorisation is 40-190 small launches whose arguments depend only on (m, n) once the
-// operands live in context-owned staging buffers; the launch sequence is captured once per shape and replayed with a
-// single API call (operands are copied in and out with three asynchronous copies).  This removes the host-side launch
-// cost, which is what limits throughput when many solver instances share one GPU.
-namespace {
-
-struct QrGraph {
-    cudaGraphExec_t exec = nullptr;
-    uint64_t gen = 0;
-    int64_t launches = 0;
-};
-std::mutex g_graph_mutex;
-std::map<std::pair<tn_ctx*, uint64_t>, QrGraph> g_graphs;
-
-bool graphs_enabled() {
-    static int on = -1;
-    // off by default: measured on B200, replay lowers the single-stream latency of an 8192 x 512 factorisation by 6 %
-    // but lowers the throughput of 8 concurrent solver instances by 30 % (set TN_QR_GRAPHS=1 to enable)
-    if (on < 0) { const char* e = getenv("TN_QR_GRAPHS"); on = (e && e[0] == '1') ? 1 : 0; }
-    return on == 1;
-}
-
-}  // namespace
-
 extern "C" int tn_qr_pos(tn_ctx* ctx, void* stream, int m, int n, double* A, int lda, double* Q, int ldq, double* R,
                          int ldr, unsigned long long* maxabs_bits) {
     TN_REQUIRE(ctx != nullptr, "null context");
     TN_REQUIRE(m >= 1 && n >= 1, "empty matrix");
     TN_REQUIRE(lda >= n && ldq >= (m < n ? m : n) && ldr >= n, "bad leading dimension");
-    cudaStream_t st = as_stream(stream);
-    const int k = m < n ? m : n;
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    cudaStreamIsCapturing(st, &cap);
-    // (the legacy default stream cannot be captured)
-    if (!graphs_enabled() || k < 32 || cap != cudaStreamCaptureStatusNone || st == nullptr || st == cudaStreamLegacy ||
-        st == cudaStreamPerThread)
-        return qr_body(ctx, st, m, n, A, lda, Q, ldq, R, ldr, maxabs_bits);
-
-    // staging buffers and every scratch slot the body touches are sized BEFORE the capture
-    const size_t nA = (size_t)m * n, nQ = (size_t)m * k, nR = (size_t)k * n;
-    double* stage = (double*)tn_scratch(ctx, TN_SLOT_STAGE, (nA + nQ + nR + 2) * sizeof(double));
-    if (!stage) return TN_ERR_NOMEM;
-    if (!tn_scratch(ctx, TN_SLOT_QR, qr_scratch_need(m, n))) return TN_ERR_NOMEM;
-    if (!tn_scratch(ctx, TN_SLOT_GEMM, (size_t)48 << 20)) return TN_ERR_NOMEM;
-    stage = (double*)ctx->scratch[TN_SLOT_STAGE];
-    double* As = stage;
-    double* Qs = As + nA;
-    double* Rs = Qs + nQ;
-    unsigned long long* bits = (unsigned long long*)(Rs + nR);
-
-    const uint64_t key = ((uint64_t)(unsigned)m << 32) | (unsigned)n;
-    QrGraph g;
-    {
-        std::lock_guard<std::mutex> lock(g_graph_mutex);
-        auto it = g_graphs.find({ctx, key});
-        if (it != g_graphs.end()) g = it->second;
-    }
-    if (!g.exec || g.gen != ctx->scratch_gen) {
-        if (g.exec) cudaGraphExecDestroy(g.exec);
-        g = QrGraph();
-        const int64_t before = ctx->launches;
-        tn_capture_lock();
-        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
-            tn_capture_unlock();
-            cudaGetLastError();
-            return qr_body(ctx, st, m, n, A, lda, Q, ldq, R, ldr, maxabs_bits);
-        }
-        ctx->capturing = true;
-        int rc = qr_body(ctx, st, m, n, As, n, Qs, k, Rs, n, bits);
-        ctx->capturing = false;
-        cudaGraph_t graph = nullptr;
-        cudaError_t e = cudaStreamEndCapture(st, &graph);
-        tn_capture_unlock();
-        if (rc || e != cudaSuccess || !graph) {
-            if (graph) cudaGraphDestroy(graph);
-            cudaGetLastError();
-            ctx->launches = before;
-            // capture not possible (e.g. a slot had to grow): run the plain launch sequence
-            return qr_body(ctx, st, m, n, A, lda, Q, ldq, R, ldr, maxabs_bits);
-        }
-        e = cudaGraphInstantiate(&g.exec, graph, 0);
-        cudaGraphDestroy(graph);
-        if (e != cudaSuccess) return tn_cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__);
-        g.gen = ctx->scratch_gen;
-        g.launches = ctx->launches - before;
-        ctx->launches = before;
-        std::lock_guard<std::mutex> lock(g_graph_mutex);
-        g_graphs[{ctx, key}] = g;
-    }
-    TN_CUDA(cudaMemcpy2DAsync(As, (size_t)n * sizeof(double), A, (size_t)lda * sizeof(double), (size_t)n * sizeof(double), m,
-                              cudaMemcpyDeviceToDevice, st));
-    TN_CUDA(cudaGraphLaunch(g.exec, st));
-    ctx->launches += g.launches;
-    TN_CUDA(cudaMemcpy2DAsync(Q, (size_t)ldq * sizeof(double), Qs, (size_t)k * sizeof(double), (size_t)k * sizeof(double), m,
-                              cudaMemcpyDeviceToDevice, st));
-    TN_CUDA(cudaMemcpy2DAsync(R, (size_t)ldr * sizeof(double), Rs, (size_t)n * sizeof(double), (size_t)n * sizeof(double), k,
-                              cudaMemcpyDeviceToDevice, st));
-    if (maxabs_bits) TN_CUDA(cudaMemcpyAsync(maxabs_bits, bits, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
-    return TN_OK;
+    // (Replaying the launch sequence as a CUDA graph was tried in both rounds: -6 % latency for a single stream, but 3x
+    // LOWER throughput with 24 solver streams -- 1.59 vs 0.48 s per instance, profiles/r2c_bench_batch_sweep.txt -- so the
+    // kernels are launched directly.)
+    return qr_body(ctx, as_stream(stream), m, n, A, lda, Q, ldq, R, ldr, maxabs_bits);
 }
 
 #ifdef TN_PHASES

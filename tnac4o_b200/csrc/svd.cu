@@ -801,11 +801,21 @@ extern "C" int tn_svd(tn_ctx* ctx, void* stream, int m, int n, const double* C, 
         TN_LAUNCHED(ctx);
         sweeps = -1;
         if (!small) {
-            // a host read-back already happened for this (large) matrix: also verify convergence
+            // a host read-back already happened for this (large) matrix: also verify convergence.  The fall-back of the
+            // reference is a second LAPACK driver (gesdd -> gesvd, mps.py:31-34); here an unconverged iteration is simply
+            // continued -- the kernel wrote its partially orthogonalised vectors back -- for up to three more launches
             int* hs = (int*)((char*)ctx->pinned + 320);
-            TN_CUDA(cudaMemcpyAsync(hs, status, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-            TN_CUDA(cudaStreamSynchronize(st));
-            sweeps = hs[0];
+            int total_sweeps = 0;
+            for (int attempt = 0; attempt < 4; ++attempt) {
+                TN_CUDA(cudaMemcpyAsync(hs, status, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+                TN_CUDA(cudaStreamSynchronize(st));
+                total_sweeps += hs[0];
+                if (hs[1] || attempt == 3) break;
+                TN_CUDA(cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel, E, ldw, a, ext, nc, (int)MAX_SWEEPS, tol, (const SvdMeta*)meta,
+                                           status, vglob));
+                TN_LAUNCHED(ctx);
+            }
+            sweeps = total_sweeps;
             if (!hs[1]) {
                 tn_set_error("Jacobi SVD of a %d x %d matrix (%d live vectors) did not converge in %d sweeps", m, n, nc, sweeps);
                 return TN_ERR_NOCONV;

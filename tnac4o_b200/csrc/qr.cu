@@ -358,25 +358,25 @@ qr_panel_smem_kernel(double* __restrict__ A, int lda, int m, int j0, int jb, dou
 // ---------------------------------------------------------------------------------------------------------------
 // T of an outer block from the inner T_p and the Gram matrix G = V^T V of the block's reflectors:
 //   T[0:J, Jblk] = -T[0:J, 0:J] * G[0:J, Jblk] * T_Jblk        (merging compact-WY factors)
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(1024, 1)
 build_outer_T_kernel(const double* __restrict__ G, int ldg, const double* __restrict__ Tin, int nbw, double* __restrict__ Tout) {
     extern __shared__ __align__(16) double sm[];
     double* T = sm;                 // [NB][NB]
     double* Y = sm + NB * NB;       // [NB][JB]
     const int tid = threadIdx.x;
-    for (int i = tid; i < NB * NB; i += 256) T[i] = 0.0;
+    for (int i = tid; i < NB * NB; i += 1024) T[i] = 0.0;
     __syncthreads();
     const int nblk = (nbw + JB - 1) / JB;
     for (int q = 0; q < nblk; ++q) {
         const int J = q * JB, jb = min(JB, nbw - J);
         const double* Tq = Tin + (size_t)q * JB * JB;
         // diagonal block
-        for (int i = tid; i < JB * JB; i += 256) {
+        for (int i = tid; i < JB * JB; i += 1024) {
             int r = i / JB, c = i % JB;
             if (r < jb && c < jb) T[(J + r) * NB + J + c] = Tq[r * JB + c];
         }
         // Y = T[0:J, 0:J] * G[0:J, Jblk]
-        for (int i = tid; i < J * JB; i += 256) {
+        for (int i = tid; i < J * JB; i += 1024) {
             int r = i / JB, c = i % JB;
             double s = 0.0;
             if (c < jb)
@@ -385,7 +385,7 @@ build_outer_T_kernel(const double* __restrict__ G, int ldg, const double* __rest
         }
         __syncthreads();
         // T[0:J, Jblk] = -Y * T_q
-        for (int i = tid; i < J * JB; i += 256) {
+        for (int i = tid; i < J * JB; i += 1024) {
             int r = i / JB, c = i % JB;
             if (c < jb) {
                 double s = 0.0;
@@ -395,7 +395,7 @@ build_outer_T_kernel(const double* __restrict__ G, int ldg, const double* __rest
         }
         __syncthreads();
     }
-    for (int i = tid; i < NB * NB; i += 256) Tout[i] = T[i];
+    for (int i = tid; i < NB * NB; i += 1024) Tout[i] = T[i];
 }
 
 __global__ void set_identity_kernel(double* Q, int ldq, int m, int k) {
@@ -648,7 +648,7 @@ static int qr_body(tn_ctx* ctx, cudaStream_t st, int m, int n, double* A, int ld
         if (nbw > JB) {
             // block reflector of the whole outer block
             if ((rc = tn_gemm_impl(ctx, st, 1, 0, nbw, nbw, mr, 1.0, Vo, k, 0, Vo, k, 0, 0.0, G, NB, 0, 1))) return rc;
-            build_outer_T_kernel<<<1, 256, tsmem, st>>>(G, NB, Tin + (size_t)pan0 * JB * JB, nbw, To);
+            build_outer_T_kernel<<<1, 1024, tsmem, st>>>(G, NB, Tin + (size_t)pan0 * JB * JB, nbw, To);
             TN_LAUNCHED(ctx);
         } else {
             // single inner panel: T_outer = T_inner (embedded with leading dimension NB)

@@ -224,7 +224,8 @@ def run_gpu(args):
     # ~0.3 s of CPU per instance for its ~10^5 launches.  Cap: 6 threads per core.
     cores = len(os.sched_getaffinity(0))
     from tnac4o_b200._native import lib as _lib, check as _check
-    _check(_lib.tn_set_blocking_sync(1))
+    WAIT_MODE = int(os.environ.get('TN_WAIT_MODE', '1'))      # 1 = sleeping waits, 2 = yield-spinning waits
+    _check(_lib.tn_set_blocking_sync(WAIT_MODE))
     _check(_lib.tn_set_throughput_mode(0 if os.environ.get('TN_THROUGHPUT') == '0' else 1))
     if world * B > 6 * cores:
         B = max(2, 6 * cores // world)
@@ -273,6 +274,7 @@ def run_gpu(args):
     barrier()
     clocks.start()
     launches0 = ops.launch_count(dev)
+    cpu0 = time.process_time()
     t_begin = time.perf_counter()
     dev_s, stats = [], []
     for _ in range(args.steps):
@@ -280,13 +282,15 @@ def run_gpu(args):
         dev_s.append(d); stats.append(st)
     barrier()
     total = time.perf_counter() - t_begin
+    cpu_per_instance = (time.process_time() - cpu0) / (args.steps * B)      # host CPU seconds this rank spent per instance
     launches = ops.launch_count(dev) - launches0
     clk = clocks.stop()
     lite = bool(os.environ.get('TN_BENCH_LITE'))          # profiler runs: timed region only
     if lite:
         if rank == 0:
             print(json.dumps({'metric': METRIC, 'value': total / (args.steps * B * world), 'unit': UNIT, 'n_gpus': world,
-                              'steps': args.steps, 'warmup': args.warmup, 'lite': True, 'gpu_launches': int(launches)}))
+                              'steps': args.steps, 'warmup': args.warmup, 'lite': True, 'gpu_launches': int(launches),
+                              'host_cpu_seconds_per_instance': cpu_per_instance}))
         if world > 1:
             dist.destroy_process_group()
         return
@@ -408,7 +412,7 @@ def run_gpu(args):
            'branch_marginals_per_s': marg_all / (total * frac_search) if frac_search else None,
            'branch_marginals_per_s_single_stream': lat_stats['marginals'] / lat_stats['seconds_search'],
            'device_seconds_per_step_rank0': float(np.mean(dev_s)),
-           'host_model_prep_seconds': t_prep,
+           'host_model_prep_seconds': t_prep, 'host_cpu_seconds_per_instance_rank0': cpu_per_instance,
            'e2e': {'value': total_e2e / (e2e_steps * world * B), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
                    'd2h_bytes_per_step': int(d2h), 'steps': e2e_steps},
            'gpu_launches': int(launches_all), 'clocks': clk, 'roofline': roofline, 'cpu_baseline': cpu}

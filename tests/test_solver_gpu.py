@@ -439,3 +439,22 @@ def test_ten_instances_reach_the_golden_energies(L, D):
         assert abs(tnac4o_b200.energy_Jij(J, ins.binary_states()[:1])[0] - ins.energy[0]) < 1e-6
         if int(ins.degeneracy) == 1:
             assert np.array_equal(ins.binary_states()[0], bits_file), (L, k)
+
+
+@pytest.mark.parametrize('L,D', [(128, 8), (512, 16)])
+def test_boundary_mps_bond_dimensions_equal_the_oracle(L, D):
+    """the rank decisions of truncateC (keep = #{S > S0 max(eps, tol)}, mps.py:805-806) on the real centre matrices: every
+    bond dimension of every row equals the oracle's (LAPACK gesdd), the overlaps agree to 1e-12 (measured 2e-15,
+    profiles/r2c_bond_probe.txt) -- so the deflation of svd.cu below 1e-2 eps ||C|| changes no kept rank here"""
+    from oracle import RefSolver
+    J = droplet_couplings(L)
+    ref = make(J, L=L, cls=RefSolver)
+    ref._setup_rhoT(Dmax=D)
+    ins = make(J, L=L)
+    ins.build_rhoT0 = True
+    ins._setup_rhoT(Dmax=D)
+    for ny in range(ins.Ny):
+        a = [ins.rhoT[ny].A[0].shape[0]] + [t.shape[2] for t in ins.rhoT[ny].A]
+        b = [ref.rhoT[ny].A[0].shape[0]] + [t.shape[2] for t in ref.rhoT[ny].A]
+        assert a == b, (ny, a, b)
+        assert abs(ins.rhoT_overlap[ny] / ref.rhoT_overlap[ny] - 1) < 1e-12

@@ -154,7 +154,9 @@ int tn_profile_read(tn_ctx* ctx, double* h_out, int ncat) {
 
 int tn_set_blocking_sync(int on) {
     // host threads waiting in a synchronising call sleep instead of spinning: many solver threads can share few cores
-    TN_CUDA(cudaSetDeviceFlags(on ? cudaDeviceScheduleBlockingSync : cudaDeviceScheduleAuto));
+    // 0: driver default (spin), 1: sleep on an interrupt (frees the core, ~0.4 ms wake-up), 2: spin with sched_yield (keeps
+    // the wake-up short while letting other runnable threads of an oversubscribed host take the core)
+    TN_CUDA(cudaSetDeviceFlags(on == 1 ? cudaDeviceScheduleBlockingSync : (on == 2 ? cudaDeviceScheduleYield : cudaDeviceScheduleAuto)));
     return TN_OK;
 }
 

@@ -53,6 +53,18 @@ void tn_capture_unlock();
         if (e__ != cudaSuccess) return tn_cuda_fail(e__, #call, __FILE__, __LINE__); \
     } while (0)
 
+// cudaFuncSetAttribute once per call site and device instead of once per launch (the call costs a few microseconds of
+// host time; the boundary-MPS build issues ~10^5 launches per instance and the host side is what limits 8-GPU scaling)
+#define TN_FUNC_ATTR_ONCE(ctx, func, attr, value)                                                    \
+    do {                                                                                             \
+        static unsigned long long done__ = 0;                                                        \
+        const unsigned long long bit__ = 1ull << ((ctx)->device & 63);                               \
+        if (!(done__ & bit__)) {                                                                     \
+            TN_CUDA(cudaFuncSetAttribute(func, attr, value));                                        \
+            done__ |= bit__;                                                                         \
+        }                                                                                            \
+    } while (0)
+
 #define TN_LAUNCHED(ctx)                                                       \
     do {                                                                       \
         (ctx)->launches++;                                                     \

@@ -202,7 +202,7 @@ int launch_cfg(tn_ctx* ctx, cudaStream_t st, int tA, int tB, int M, int N, int K
 #define TN_GEMM_LAUNCH(AK, BKc)                                                                                        \
     do {                                                                                                               \
         auto kern = gemm_kernel<BM, BN, WM, WN, AK, BKc>;                                                              \
-        TN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
+        TN_FUNC_ATTR_ONCE(ctx, kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                         \
         kern<<<grid, THREADS, smem, st>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, splitk, kchunk,    \
                                           partial, bmap);                                                              \
     } while (0)

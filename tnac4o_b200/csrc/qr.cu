@@ -618,7 +618,7 @@ static int qr_body(tn_ctx* ctx, cudaStream_t st, int m, int n, double* A, int ld
     double* W2 = W + (size_t)NB * wcols;
     double* WY = W2 + (size_t)NB * wcols;
     const size_t tsmem = ((size_t)NB * NB + (size_t)NB * JB) * sizeof(double);
-    TN_CUDA(cudaFuncSetAttribute(build_outer_T_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+    TN_FUNC_ATTR_ONCE(ctx, build_outer_T_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
     int rc;
     for (int ob = 0; ob < nouter; ++ob) {
         const int J0 = ob * NB, nbw = (k - J0) < NB ? (k - J0) : NB;

@@ -613,7 +613,7 @@ int tn_marginals(tn_ctx* ctx, void* stream, const tn_site* site, int nb, int Dr,
     }
     size_t smem = ((size_t)site->nd * Dr + (size_t)Dr * site->nr + (size_t)site->nd * site->nr) * sizeof(double);
     TN_REQUIRE(smem <= 220 * 1024, "bond dimension too large for marginals shared memory");
-    TN_CUDA(cudaFuncSetAttribute(marginals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    TN_FUNC_ATTR_ONCE(ctx, marginals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     int grid = nb < 8 * ctx->sm_count ? nb : 8 * ctx->sm_count;
     marginals_kernel<<<grid, 256, smem, st>>>(nb, site->nS, site->nl, site->nd, site->nr, site->nu, Dr, site->Wlu,
                                               site->dmap, site->rmap, T1, RR, root, vind, vstride, nx, prob, cand, flag,

@@ -731,7 +731,7 @@ extern "C" int tn_svd(tn_ctx* ctx, void* stream, int m, int n, const double* C, 
         if (nc > 1) {
             int bsz = (nc + 1) / 2;
             size_t smem = (size_t)nc * ldw * sizeof(double);
-            TN_CUDA(cudaFuncSetAttribute(jacobi_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+            TN_FUNC_ATTR_ONCE(ctx, jacobi_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
             TN_CUDA(cudaMemsetAsync(rot, 0, sizeof(unsigned int), st));
             jacobi_round_kernel<<<1, JT, smem, st>>>(E, ldw, a, nc, bsz, 2, 0, MAX_SWEEPS, tol, meta, rot);
             TN_LAUNCHED(ctx);
@@ -742,7 +742,7 @@ extern "C" int tn_svd(tn_ctx* ctx, void* stream, int m, int n, const double* C, 
         const int halfp = (nc + 1) / 2;
         size_t ll = ((size_t)ceil_div(a, ncl2) + (size_t)ceil_div(ext, ncl2)) | 1;
         size_t smem = (size_t)nc * ll * sizeof(double) + (ncl2 > 1 ? (size_t)2 * ncl2 * halfp * 3 * sizeof(double) : 0);
-        TN_CUDA(cudaFuncSetAttribute(jacobi_cluster2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CL_SMEM));
+        TN_FUNC_ATTR_ONCE(ctx, jacobi_cluster2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CL_SMEM);
         if (ncl2 > CLJ) TN_CUDA(cudaFuncSetAttribute(jacobi_cluster2_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(ncl2, 1, 1);
@@ -782,8 +782,8 @@ extern "C" int tn_svd(tn_ctx* ctx, void* stream, int m, int n, const double* C, 
         const int vglob = (ncl == CLJ_MAX && !fits16) ? 1 : 0;
         size_t ll = ((size_t)ceil_div(a, ncl) + (vglob ? 0 : (size_t)ceil_div(ext, ncl))) | 1;
         size_t smem = (size_t)nc * ll * sizeof(double);
-        TN_CUDA(cudaFuncSetAttribute(jacobi_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CL_SMEM));
-        TN_CUDA(cudaFuncSetAttribute(jacobi_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        TN_FUNC_ATTR_ONCE(ctx, jacobi_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CL_SMEM);
+        TN_FUNC_ATTR_ONCE(ctx, jacobi_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(ncl, 1, 1);
         cfg.blockDim = dim3(JT, 1, 1);

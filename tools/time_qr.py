@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from tnac4o_b200 import ops
 dev = torch.device('cuda', 0)
-torch.cuda.set_stream(torch.cuda.Stream())      # a non-default stream: the QR launch sequence is replayed as a CUDA graph
+torch.cuda.set_stream(torch.cuda.Stream())      # a non-default stream, as the solver threads use
 rng = np.random.default_rng(0)
 def timeit(f, reps=30):
     for _ in range(3): f()

@@ -867,6 +867,25 @@ class tnac4o:
                                ptr(ws['Enew']), ptr(ws['Pnew']), ptr(ws['parent']), ptr(ws['cell']), ptr(old.states),
                                float(max_dEng), int(lim_hd) if self.mode == 'Ising' else -int(lim_hd)))
 
+    @staticmethod
+    def _materialise_pools(dE, dP, key, first, last, cptr, ccnt, cnode, cbud, roots):
+        """node / children pools of csrc/droplet_book.cu -> the reference's nested tuples ((dE, key, first, last, dlogP),
+        sub-excitations).  A child entry (node, budget) stands for _exc_cut_energy(node, budget) (tnac4o.py:2071-2079): its
+        own children are kept while dE <= budget and viewed with min(their stored budget, budget - dE) -- nested prunings
+        compose to exactly what the reference's eager recursion leaves.  Returns (list of trees, set of keys used)."""
+        used = set()
+
+        def build(n, budget):
+            used.add(int(key[n]))
+            kids = []
+            for e in range(cptr[n], cptr[n] + ccnt[n]):
+                ch = cnode[e]
+                if dE[ch] <= budget:
+                    kids.append(build(ch, min(cbud[e], budget - dE[ch])))
+            return ((dE[n], int(key[n]), int(first[n]), int(last[n]), dP[n]), tuple(kids))
+
+        return [build(int(n), np.inf) for n in roots], used
+
     def _book_open(self, M):
         c = Context.get(self._dev())
         handle = ctypes.c_void_p()
@@ -893,18 +912,7 @@ class tnac4o:
         self._book = None
         self.stats['droplet_pairs'] = npairs
         self.stats['droplet_nodes'] = nn
-        used = set()
-
-        def build(n, budget):
-            used.add(int(key[n]))
-            kids = []
-            for e in range(cptr[n], cptr[n] + ccnt[n]):
-                ch = cnode[e]
-                if dE[ch] <= budget:
-                    kids.append(build(ch, min(cbud[e], budget - dE[ch])))
-            return ((dE[n], int(key[n]), int(first[n]), int(last[n]), dP[n]), tuple(kids))
-
-        self.el = [build(int(n), np.inf) for n in list0[:n0]]
+        self.el, used = self._materialise_pools(dE, dP, key, first, last, cptr, ccnt, cnode, cbud, list0[:n0])
         self.d, self.invd = {}, {}
         for k in sorted(used):
             dpos = spos[sptr[k]:sptr[k + 1]].astype(np.int64)

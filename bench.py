@@ -347,9 +347,10 @@ def run_gpu(args):
                 'device_seconds_all_primitives': allsec, 'dominant_primitive_by_device_time': dominant,
                 'per_primitive': per, 'instrumented_instance_seconds': t_pass,
                 'hbm_peak_gbs': hbm_peak,
-                'note': 'achieved = algorithmic flops of the reference schedule that were executed (QR 4mn^2 - 4n^3/3 incl. forming Q, SVD 22k^3 '
-                        'with vectors / 8k^3/3 without, GEMM 2MNK, right environments) / device time of those primitives, single instance, '
-                        'one stream; QR panels and Jacobi rounds run on the non-tensor FP64 pipe (measured ~15 FMA/clk/SM, '
+                'note': 'achieved / frac = algorithmic flops of the reference schedule that were executed (QR 4mn^2 - 4n^3/3 incl. forming Q, '
+                        'SVD 22k^3 with vectors / 8k^3/3 without, GEMM 2MNK, right environments) x instances x steps / wall time of the timed '
+                        'region (all concurrent instances, all GPUs); single_instance and per_primitive = the same flops / device time of '
+                        'the primitives of ONE instance alone on one stream (library timers); QR panels and Jacobi rounds run on the non-tensor FP64 pipe (measured ~15 FMA/clk/SM, '
                         'profiles/r2a_qr_panel_phase_cycles_and_svd_timings.txt) and are latency-bound, the GEMMs run on DMMA',
                 'peak_source': 'measured here: torch.matmul f64 8192^3 (cuBLAS DGEMM), best of 5 -- MEASURED_PEAKS.json has no FP64 entry',
                 'measured_in': 'one extra single-instance step on the native path right after the timed region, library timers on '
@@ -393,6 +394,13 @@ def run_gpu(args):
         synth_ok = synth_ok and bool(abs(tnac4o_b200.energy_Jij(Ji, x.binary_states()[:1])[0] - x.energy[0]) < 1e-6)
     if roofline is not None and roofline.get('algorithmic_gflop_per_instance'):
         whole = roofline['algorithmic_gflop_per_instance'] * 1e9 * instances / total / 1e12
+        # top level = the TIMED REGION: algorithmic flops of all instances of all steps / wall time of the timed region,
+        # against the FP64 tensor peak of the GPUs used; the single-instance figures of the instrumented pass stay beside it
+        roofline['single_instance'] = {'achieved': roofline['achieved'], 'frac': roofline['frac'],
+                                       'device_seconds_contraction': roofline['device_seconds_contraction']}
+        roofline['achieved'] = whole
+        roofline['frac'] = whole / (roofline['peak'] * world)
+        roofline['peak_all_gpus'] = roofline['peak'] * world
         roofline['whole_step_tflops'] = whole
         roofline['whole_step_frac_fp64_tensor_peak'] = whole / (roofline['peak'] * world)
 

@@ -25,6 +25,8 @@ Fixtures
   ref_j124_sweep.npz  examples/e06 on J124 C=8 instances 1-20: per rotation energy / degeneracy and the selected pair,
                       with the couplings and the lines of results_*J124*.txt
   ref_rmf.npz         examples/e05 (RMF toy 5x3): spectra for the three encodings (test_examples.py:107-136)
+  ref_noise.npz       host logic: couplings of L=128 #1 (and of a 8x2 lattice) after rotate_graph(rot) and add_noise with
+                      np.random.seed(7), as sorted (row, col, value) triplets, plus the cell order
 """
 import os
 import sys
@@ -370,6 +372,23 @@ def make_j124():
     np.savez_compressed(os.path.join(HERE, 'ref_j124.npz'), **out)
 
 
+def make_noise():
+    out = {}
+    for shape in ((4, 4), (8, 2)):
+        for rot in (0, 1, 2, 3):
+            ins = ref.tnac4o(mode='Ising', Nx=shape[0], Ny=shape[1], Nc=8, J=droplet_J(128, 1), beta=3)
+            if rot:
+                ins.rotate_graph(rot=rot)
+            np.random.seed(7)
+            ins.add_noise(amplitude=1e-7)
+            c = ins.J.tocoo()
+            k = np.lexsort((c.col, c.row))
+            tag = 'n_%dx%d_r%d_' % (shape[0], shape[1], rot)
+            out[tag + 'row'], out[tag + 'col'], out[tag + 'val'] = c.row[k].astype(np.int32), c.col[k].astype(np.int32), c.data[k]
+            out[tag + 'order'] = np.asarray(ins.order)
+    np.savez_compressed(os.path.join(HERE, 'ref_noise.npz'), **out)
+
+
 if __name__ == '__main__':
     for what in sys.argv[1:]:
         t0 = time.time()
@@ -379,5 +398,5 @@ if __name__ == '__main__':
          'l2048m4096': lambda: make_big(2048, 32, 4096, 'ref_l2048_m4096.npz'),
          'gibbs2048': make_gibbs_l2048, 'encodings': make_encodings, 'saved': make_saved_files,
          'l1152': make_l1152, 'l1152saved': make_l1152_saved, 'j124': make_j124, 'j124sweep': make_j124_sweep,
-         'rmf': make_rmf}[what]()
+         'rmf': make_rmf, 'noise': make_noise}[what]()
         print(what, 'done in %.1f s' % (time.time() - t0), flush=True)

@@ -108,3 +108,27 @@ def test_rotate_graph_host_logic_matches_oracle():
             assert np.array_equal(a.sd, b.sd) and np.array_equal(a.sr, b.sr)
             offs = a._key_offsets(a.Ny - 1, a.Nx - 1)                  # merge-key layout stays within 128 bits
             assert len(offs) == a.Nx + 1 and int(offs[-1]) < 128
+
+
+def test_rotate_then_add_noise_matches_reference_fixture():
+    """add_noise (tnac4o.py:917-941) draws one uniform per stored coupling in storage order: with the same global-RNG seed
+    the couplings equal the reference's bit for bit, also after quarter turns (which rebuild the sparse matrix here) and on
+    a non-square lattice; fixture written by the reference (tests/golden/make_golden.py noise)"""
+    import numpy as np
+    import tnac4o_b200
+    from conftest import droplet_couplings, golden
+    z = golden('ref_noise.npz')
+    J = droplet_couplings(128)
+    for shape in ((4, 4), (8, 2)):
+        for rot in (0, 1, 2, 3):
+            a = tnac4o_b200.tnac4o(mode='Ising', Nx=shape[0], Ny=shape[1], Nc=8, J=J, beta=3)
+            if rot:
+                a.rotate_graph(rot)
+            np.random.seed(7)
+            a.add_noise(amplitude=1e-7)
+            c = a.J.tocoo()
+            k = np.lexsort((c.col, c.row))
+            tag = 'n_%dx%d_r%d_' % (shape[0], shape[1], rot)
+            assert np.array_equal(c.row[k], z[tag + 'row']) and np.array_equal(c.col[k], z[tag + 'col'])
+            assert np.array_equal(c.data[k], z[tag + 'val'])
+            assert np.array_equal(a.order, z[tag + 'order'])

@@ -116,27 +116,33 @@ class tnac4o:
         self._sites = None
         self._host = None
 
+    @staticmethod
+    def _quarter_turn(Nx, Ny):
+        """cell permutation of one quarter turn: cell a = ny * Nx + nx moves to turned[a] = (Nx - 1 - nx) * Ny + ny of the
+        Ny-wide rotated lattice; returns (turned, back) with back[turned] = arange"""
+        ny, nx = np.divmod(np.arange(Nx * Ny), Nx)
+        turned = (Nx - 1 - nx) * Ny + ny
+        back = np.empty_like(turned)
+        back[turned] = np.arange(Nx * Ny)
+        return turned, back
+
     def rotate_graph(self, rot=1):
-        """quarter turns of the lattice, cumulative (tnac4o.py:290-340)"""
+        """quarter turns of the lattice, cumulative (tnac4o.py:290-340): every turn relabels the spins by the cell
+        permutation, folds the coupling matrix back to its upper triangle and composes the cell order"""
         if self.mode == 'RMF':
             return self._rotate_rmf(rot)
         for _ in range(rot):
+            turned, back = self._quarter_turn(self.Nx, self.Ny)
+            # rotated J[i, j] = J[where[i], where[j]] with where = spin k of cell a -> spin k of cell turned[a]
+            where = (turned[:, None] * self.Nc + np.arange(self.Nc)).ravel()
+            Jc = scipy.sparse.coo_matrix(self.J)
+            to = np.empty(self.L, dtype=np.int64)
+            to[where] = np.arange(self.L)
+            r, c = to[Jc.row], to[Jc.col]
+            self.J = scipy.sparse.csr_matrix((Jc.data, (np.minimum(r, c), np.maximum(r, c))), shape=Jc.shape)
+            self.Nx, self.Ny = self.Ny, self.Nx
+            self.order = back[self.order]
             self.rotation += 1
-            Nx, Ny, Nc = self.Nx, self.Ny, self.Nc
-            spin_map = np.arange(self.L)
-            order = np.arange(Nx * Ny)
-            order_i = np.arange(Nx * Ny)
-            for nx in range(Nx):
-                for ny in range(Ny):
-                    src = (ny * Nx + nx) * Nc + np.arange(Nc)
-                    dst = ((Nx - nx - 1) * Ny + ny) * Nc + np.arange(Nc)
-                    spin_map[src] = dst
-                    a, b = ny * Nx + nx, (Nx - nx - 1) * Ny + ny
-                    order[a], order_i[b] = b, a
-            self.Nx, self.Ny = Ny, Nx
-            self.J = self.J[spin_map, :][:, spin_map]
-            self.J = scipy.sparse.triu(self.J) + scipy.sparse.tril(self.J, -1).T
-            self.order = order_i[self.order]
         self.order_i[self.order] = np.arange(self.Nx * self.Ny)
         self.rotation = np.mod(self.rotation, 4)
         self._divide_couplings()
@@ -145,42 +151,31 @@ class tnac4o:
         """site (ny, nx) -> (Nx - 1 - nx, ny): factor keys, sizes and the cell order (tnac4o.py:315-336)"""
         for _ in range(rot):      # (the reference does not advance `rotation` in this mode; kept: it only labels outputs)
             Nx, Ny = self.Nx, self.Ny
+            turned, _ = self._quarter_turn(Nx, Ny)
             turn = lambda ny, nx: (Nx - nx - 1, ny)
-            fac = {}
-            for key, val in self.J['fac'].items():
-                fac[turn(*key) if len(key) == 2 else turn(*key[:2]) + turn(*key[2:])] = val
-            sizes = np.zeros((Nx, Ny), dtype=int)
-            order_i = np.arange(Nx * Ny)
-            for nx in range(Nx):
-                for ny in range(Ny):
-                    sizes[Nx - nx - 1, ny] = self.Nrmf[ny, nx]
-                    order_i[ny * Nx + nx] = (Nx - nx - 1) * Ny + ny
+            self.J['fac'] = {(turn(*key) if len(key) == 2 else turn(*key[:2]) + turn(*key[2:])): val
+                             for key, val in self.J['fac'].items()}
+            self.Nrmf = np.ascontiguousarray(np.asarray(self.Nrmf)[:, ::-1].T)      # sizes[Nx - 1 - nx, ny] = N[ny, nx]
             self.Nx, self.Ny = Ny, Nx
-            self.order = order_i[self.order]
-            self.J['fac'] = fac
-            self.Nrmf = sizes
+            self.order = turned[self.order]          # (this mode composes with the forward map, as the reference does)
         self.order_i[self.order] = np.arange(self.Nx * self.Ny)
         self.rotation = np.mod(self.rotation, 4)
         self._divide_couplings()
 
     def add_noise(self, amplitude=1e-7):
-        """tnac4o.py:917-941 (consumes the global numpy RNG like the reference)"""
+        """uniform noise in [-amplitude, amplitude] on every stored coupling / every one-site RMF function
+        (tnac4o.py:917-941; consumes the global numpy RNG in the reference's order: stored entries row by row)"""
         self.logger.info('Adding noise to the coupling with ampliture %.2e', amplitude)
+        draw = lambda n: (np.random.rand(n) * 2 - 1) * amplitude
         if self.mode == 'RMF':
-            fun = {}
-            for key, value in self.J['fun'].items():
-                fun[key] = np.array(value, dtype=float)
-                if fun[key].ndim == 1:
-                    fun[key] += ((np.random.rand(fun[key].shape[0]) * 2 - 1) * amplitude)
+            fun = {key: np.array(value, dtype=float) for key, value in self.J['fun'].items()}
+            for f in fun.values():
+                if f.ndim == 1:
+                    f += draw(f.shape[0])
             self.J['fun'] = fun
-            self._divide_couplings()
-            return
-        nzr = self.J.nonzero()
-        kk = ((np.random.rand(len(nzr[0])) * 2 - 1) * amplitude)
-        self.J = scipy.sparse.lil_matrix(self.J)
-        for i, j, k in zip(nzr[0], nzr[1], kk):
-            self.J[i, j] += k
-        self.J = scipy.sparse.csr_matrix(self.J)
+        else:
+            rows, cols = self.J.nonzero()
+            self.J = scipy.sparse.csr_matrix(self.J + scipy.sparse.csr_matrix((draw(len(rows)), (rows, cols)), shape=self.J.shape))
         self._divide_couplings()
 
     # ------------------------------------------------------------------ device tables

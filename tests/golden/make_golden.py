@@ -25,6 +25,7 @@ Fixtures
   ref_j124_sweep.npz  examples/e06 on J124 C=8 instances 1-20: per rotation energy / degeneracy and the selected pair,
                       with the couplings and the lines of results_*J124*.txt
   ref_rmf.npz         examples/e05 (RMF toy 5x3): spectra for the three encodings (test_examples.py:107-136)
+  ref_max_energy.npz  known answers of max_energy_otn2d.txt (L=128 #1-3) and the reference's search on minus_Jij(J) for them
   ref_noise.npz       host logic: couplings of L=128 #1 (and of a 8x2 lattice) after rotate_graph(rot) and add_noise with
                       np.random.seed(7), as sorted (row, col, value) triplets, plus the cell order
 """
@@ -372,6 +373,20 @@ def make_j124():
     np.savez_compressed(os.path.join(HERE, 'ref_j124.npz'), **out)
 
 
+def make_max_energy():
+    out = {}
+    fn = '%s/Chimera_droplet_instances/chimera128_spinglass_power/max_energy_otn2d.txt' % INST
+    lines = {l.split(':')[0].strip(): l.split(':')[1].split() for l in open(fn)}
+    for k in (1, 2, 3):
+        vals = lines['%03d.txt' % k]
+        out['file_%03d_energy' % k], out['file_%03d_bits' % k] = float(vals[0]), np.array(vals[1:], dtype=np.int8)
+        ins = ref.tnac4o(mode='Ising', Nx=4, Ny=4, Nc=8, J=ref.minus_Jij(droplet_J(128, k)), beta=3)
+        ins.search_ground_state(M=2 ** 10, relative_P_cutoff=1e-8, Dmax=48)
+        result_fields(ins, 'max_%03d' % k, out)
+        out['max_%03d_bits' % k] = ins.binary_states()[0].astype(np.int8)
+    np.savez_compressed(os.path.join(HERE, 'ref_max_energy.npz'), **out)
+
+
 def make_noise():
     out = {}
     for shape in ((4, 4), (8, 2)):
@@ -398,5 +413,5 @@ if __name__ == '__main__':
          'l2048m4096': lambda: make_big(2048, 32, 4096, 'ref_l2048_m4096.npz'),
          'gibbs2048': make_gibbs_l2048, 'encodings': make_encodings, 'saved': make_saved_files,
          'l1152': make_l1152, 'l1152saved': make_l1152_saved, 'j124': make_j124, 'j124sweep': make_j124_sweep,
-         'rmf': make_rmf, 'noise': make_noise}[what]()
+         'rmf': make_rmf, 'noise': make_noise, 'maxenergy': make_max_energy}[what]()
         print(what, 'done in %.1f s' % (time.time() - t0), flush=True)

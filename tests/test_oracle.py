@@ -159,3 +159,22 @@ def test_adjacency_encodings_L512(ee):
     assert np.array_equal(ins.states[order], z['L512_ee%d_states' % ee])
     assert np.array_equal(ins.states[order], z['L512_ee1_states'])           # the encodings agree on the spectrum
     np.testing.assert_allclose(ins.energy[order], z['L512_ee%d_energy' % ee], atol=1e-10)
+
+
+@pytest.mark.parametrize('k', [1, 2, 3])
+def test_max_energy_known_answers(k):
+    """max_energy_otn2d.txt (the known-answer file for the sign-flipped problem, minus_Jij): the oracle on -J reaches the
+    file's energy and state, and equals the reference's own run on the same couplings (ref_max_energy.npz)"""
+    import tnac4o_b200
+    z = golden('ref_max_energy.npz')
+    J = tnac4o_b200.minus_Jij(droplet_couplings(128, k))
+    ins = run_gs(J, 0, False, 48, 1024)
+    tag = 'max_%03d' % k
+    assert abs(-ins.energy[0] - float(z['file_%03d_energy' % k])) < 1e-5
+    assert np.array_equal(ins.binary_states()[0], z['file_%03d_bits' % k])
+    assert abs(ins.energy[0] - z[tag + '_energy'][0]) < 1e-10
+    assert np.array_equal(ins.states, z[tag + '_states'])
+    np.testing.assert_allclose(ins.probability, z[tag + '_probability'], rtol=1e-8)
+    np.testing.assert_allclose(ins.discarded_probability, z[tag + '_discarded'], rtol=1e-8)
+    # the sign-flipped couplings evaluated on the file's state give minus the file's energy
+    assert abs(energy_ising_sparse(J, z['file_%03d_bits' % k][None, :])[0] + float(z['file_%03d_energy' % k])) < 1e-5

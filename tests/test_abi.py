@@ -132,3 +132,14 @@ def test_rotate_then_add_noise_matches_reference_fixture():
             assert np.array_equal(c.row[k], z[tag + 'row']) and np.array_equal(c.col[k], z[tag + 'col'])
             assert np.array_equal(c.data[k], z[tag + 'val'])
             assert np.array_equal(a.order, z[tag + 'order'])
+
+
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md maps every function include/tnac4o_b200.h declares to the reference interface it replaces"""
+    import re
+    from conftest import ROOT
+    hdr = open(os.path.join(ROOT, 'include', 'tnac4o_b200.h')).read()
+    doc = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    declared = set(re.findall(r'\b(tn_[a-z0-9_]+)\s*\(', hdr))
+    assert len(declared) > 40
+    assert sorted(n for n in declared if n not in doc) == []

@@ -39,3 +39,19 @@ def test_reference_defaults_and_file_name():
     # the name the reference's e03 gives its saved spectrum
     assert os.path.basename(e03.file_name(a, 'results')) == \
         'L=1152_ins=001_r=0_beta=3.00_D=48_M=1024_P=1.00e-08_ee=1_dE=1.000_hd=0_pre=1.npy'
+
+
+def test_instance_loading_matches_fixture():
+    """examples/_common.droplet_couplings reads an instance file the way the reference's e01:57-65 does; the committed
+    fixture holds the same couplings (skipped where the reference's instances/ folder is absent, e.g. on the GPU box)"""
+    inst = '/root/reference/instances'
+    if not os.path.isdir(inst):
+        pytest.skip('no instances/ folder here')
+    from conftest import droplet_couplings
+    sys.path.insert(0, EX)
+    try:
+        import _common
+    finally:
+        sys.path.remove(EX)
+    a = _common.parser('x').parse_args(['--instances', inst, '-L', '128', '-ins', '1'])
+    assert _common.droplet_couplings(a) == droplet_couplings(128, 1)

@@ -42,8 +42,8 @@ def test_no_cpu_fallback():
 def test_product_does_not_import_oracle():
     code = "import sys; import tnac4o_b200; assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)"
     subprocess.run([sys.executable, '-c', code], check=True, cwd=ROOT)
-    # nor does anything under include/ or tools/ (checker scripts that execute the oracle live under tests/tools/)
-    for top in ('tnac4o_b200', 'include', 'tools'):
+    # nor does anything under include/, tools/ or examples/ (checker scripts that execute the oracle live under tests/tools/)
+    for top in ('tnac4o_b200', 'include', 'tools', 'examples'):
         for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
             for f in files:
                 if f.endswith(('.py', '.cu', '.cuh', '.h')):
